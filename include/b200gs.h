@@ -1,0 +1,132 @@
+/*
+ * b200gs.h -- C ABI of the B200-native 3D Gaussian Splatting rasterizer (libb200gs.so).
+ *
+ * This is the drop-in boundary for the hot path named by BASELINE.json:north_star.  The reference
+ * repository (Maxwell-Zhao/RoboSimGS) contains no rasterizer of its own: it delegates background
+ * 3DGS reconstruction to Nerfstudio (/root/reference/README.md:75) and its per-frame datagen
+ * renderer is unreleased (/root/reference/README.md:29,85).  The interface replaced here is
+ * therefore the one north_star names -- the pybind module `_C` of the public
+ * diff-gaussian-rasterization package (un-vendored third-party code):
+ *
+ *     _C.rasterize_gaussians(...)           ->  b200gs_forward()
+ *     _C.rasterize_gaussians_backward(...)  ->  b200gs_backward()
+ *     _C.mark_visible(...)                  ->  b200gs_mark_visible()
+ *
+ * Plain pointers and sizes only; no torch types.  All `const float*` / `float*` data arguments are
+ * DEVICE pointers (contiguous fp32, row-major), exactly the buffers the Python operator surface
+ * (GaussianRasterizer.forward) already holds.  `stream` is a cudaStream_t
+ * passed as void* (NULL = legacy default stream).  The library keeps no global state besides a
+ * thread-local error string and is re-entrant per stream.
+ *
+ * Scratch memory is caller-owned: the library asks the caller to size
+ * byte buffers through a callback and carves 128-byte aligned sub-arrays inside them.  The three
+ * forward buffers must be handed back unchanged to b200gs_backward().
+ */
+#ifndef B200GS_H
+#define B200GS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200GS_VERSION 100
+
+/* Error codes (0 = success).  b200gs_last_error() returns the message for the calling thread. */
+#define B200GS_OK 0
+#define B200GS_ERR_INVALID_ARG (-1)
+#define B200GS_ERR_ALLOC (-2)
+#define B200GS_ERR_CUDA (-3)
+
+/*
+ * Per-call camera/config -- the scalar fields of GaussianRasterizationSettings (SURVEY.md 8(a)
+ * row a1).  The small tensors of the settings tuple (bg, viewmatrix, projmatrix, campos) stay on
+ * the device and are passed as pointers to b200gs_forward/backward, so a call never forces a
+ * device->host copy of the camera.
+ */
+typedef struct B200GSParams {
+  int32_t P;              /* number of Gaussians */
+  int32_t sh_degree;      /* active SH degree, 0..3 */
+  int32_t M;              /* SH coefficients stored per Gaussian per channel (shs is [P][M][3]) */
+  int32_t image_height;
+  int32_t image_width;
+  float tanfovx;
+  float tanfovy;
+  float scale_modifier;
+  int32_t prefiltered;    /* accepted for signature parity; culled Gaussians are simply skipped */
+  int32_t debug;          /* !=0: synchronise and check for errors after every kernel */
+} B200GSParams;
+
+/* Caller-owned growable byte buffer: resize(ctx, nbytes) returns a device pointer to at least
+ * nbytes (the reference binding's `std::function<char*(size_t)>` resize callbacks). */
+typedef struct B200GSAlloc {
+  void* ctx;
+  char* (*resize)(void* ctx, size_t nbytes);
+} B200GSAlloc;
+
+/*
+ * Forward: projection + SH colour, tile binning + sort, per-tile front-to-back compositing.
+ *
+ *   bg[3], viewmatrix[16], projmatrix[16], campos[3]   device; matrices TRANSPOSED (column-major)
+ *   means3D[P][3]; shs[P][M][3] or NULL; colors_precomp[P][3] or NULL (exactly one of the two)
+ *   opacities[P]; scales[P][3] + rotations[P][4] (w,x,y,z; used as given) or cov3D_precomp[P][6]
+ *   out_color[3][H][W]; radii[P] (int32, 0 = culled)
+ *   geom/binning/img: scratch allocators; *num_rendered receives the number of (Gaussian, tile)
+ *   pairs D that were sorted and composited.
+ *
+ * One device->host read (of D, to size the binning buffer) synchronises the stream, as in the
+ * interface this replaces.
+ */
+int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewmatrix,
+                   const float* projmatrix, const float* campos, const float* means3D,
+                   const float* shs, const float* colors_precomp, const float* opacities,
+                   const float* scales, const float* rotations, const float* cov3D_precomp,
+                   float* out_color, int32_t* radii, B200GSAlloc geom, B200GSAlloc binning,
+                   B200GSAlloc img, int32_t* num_rendered, void* stream);
+
+/*
+ * Backward: adjoint of the whole forward w.r.t. (means3D, shs | colors_precomp, opacities,
+ * scales, rotations | cov3D_precomp) plus the screen-space mean gradient the densification
+ * heuristics read (dL_dmeans2D, NDC-scaled units, z component 0).
+ *
+ *   geom/binning/img: the byte buffers produced by the matching forward call (device pointers)
+ *   dL_dout_color[3][H][W]
+ *   outputs (every element is written; pass NULL for tensors of the unused input alternative):
+ *     dL_dmeans3D[P][3], dL_dmeans2D[P][3], dL_dshs[P][M][3], dL_dcolors_precomp[P][3],
+ *     dL_dopacities[P], dL_dscales[P][3], dL_drotations[P][4], dL_dcov3D[P][6]
+ *   scratch: allocator for the per-Gaussian screen-space accumulators (48 B per Gaussian)
+ */
+int b200gs_backward(const B200GSParams* prm, const float* bg, const float* viewmatrix,
+                    const float* projmatrix, const float* campos, const float* means3D,
+                    const float* shs, const float* colors_precomp, const float* opacities,
+                    const float* scales, const float* rotations, const float* cov3D_precomp,
+                    const int32_t* radii, const char* geom, const char* binning, const char* img,
+                    int32_t num_rendered, const float* dL_dout_color, float* dL_dmeans3D,
+                    float* dL_dmeans2D, float* dL_dshs, float* dL_dcolors_precomp,
+                    float* dL_dopacities, float* dL_dscales, float* dL_drotations,
+                    float* dL_dcov3D, B200GSAlloc scratch, void* stream);
+
+/* present[i] = 1 iff Gaussian i passes the near-plane cull (view-space z > 0.2). */
+int b200gs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
+                        const float* projmatrix, uint8_t* present, void* stream);
+
+/* Sizes of the forward scratch buffers for given P, H, W (geom, img) and D (binning); lets a
+ * caller pre-size arenas.  Any of the out pointers may be NULL. */
+int b200gs_buffer_sizes(int32_t P, int32_t image_height, int32_t image_width, int64_t D,
+                        size_t* geom_bytes, size_t* binning_bytes, size_t* img_bytes);
+
+/* Message of the last error raised on the calling thread ("" if none). */
+const char* b200gs_last_error(void);
+
+/* B200GS_VERSION the library was built from. */
+int b200gs_version(void);
+
+/* Kernel launches issued by this process since the last call with reset != 0 (bench accounting). */
+int64_t b200gs_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200GS_H */

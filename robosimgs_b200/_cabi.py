@@ -1,0 +1,82 @@
+"""ctypes binding of libb200gs.so (include/b200gs.h).
+
+The product path has no CPU fallback: if the CUDA library is missing or cannot be loaded this
+module raises, loudly, at first use.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libb200gs.so")
+
+EXPORTED_SYMBOLS = (
+    "b200gs_forward", "b200gs_backward", "b200gs_mark_visible", "b200gs_buffer_sizes",
+    "b200gs_last_error", "b200gs_version", "b200gs_launch_count",
+)
+
+
+class B200GSParams(C.Structure):
+    _fields_ = [
+        ("P", C.c_int32), ("sh_degree", C.c_int32), ("M", C.c_int32),
+        ("image_height", C.c_int32), ("image_width", C.c_int32),
+        ("tanfovx", C.c_float), ("tanfovy", C.c_float), ("scale_modifier", C.c_float),
+        ("prefiltered", C.c_int32), ("debug", C.c_int32),
+    ]
+
+
+RESIZE_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
+
+
+class B200GSAlloc(C.Structure):
+    _fields_ = [("ctx", C.c_void_p), ("resize", RESIZE_FN)]
+
+
+_lib = None
+
+
+class B200GSError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libb200gs.so; raise if the CUDA extension has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200GSError(
+            f"{LIB_PATH} not found: the CUDA extension is not built. Run "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). "
+            "There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, fp = C.c_void_p, C.c_void_p
+    L.b200gs_forward.restype = C.c_int
+    L.b200gs_forward.argtypes = [C.POINTER(B200GSParams), fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, fp,
+                                 fp, vp, B200GSAlloc, B200GSAlloc, B200GSAlloc,
+                                 C.POINTER(C.c_int32), vp]
+    L.b200gs_backward.restype = C.c_int
+    L.b200gs_backward.argtypes = [C.POINTER(B200GSParams), fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, fp,
+                                  vp, vp, vp, vp, C.c_int32, fp,
+                                  fp, fp, fp, fp, fp, fp, fp, fp, B200GSAlloc, vp]
+    L.b200gs_mark_visible.restype = C.c_int
+    L.b200gs_mark_visible.argtypes = [C.c_int32, fp, fp, fp, vp, vp]
+    L.b200gs_buffer_sizes.restype = C.c_int
+    L.b200gs_buffer_sizes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64,
+                                      C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    L.b200gs_last_error.restype = C.c_char_p
+    L.b200gs_version.restype = C.c_int
+    L.b200gs_launch_count.restype = C.c_int64
+    L.b200gs_launch_count.argtypes = [C.c_int]
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise B200GSError(f"libb200gs error {rc}: {lib().b200gs_last_error().decode()}")
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(lib().b200gs_launch_count(1 if reset else 0))

@@ -1,0 +1,315 @@
+// api.cu -- the C ABI of libb200gs (include/b200gs.h): argument checks, scratch carving and the
+// forward / backward launch sequences.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <atomic>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace b200gs {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};  // process-wide: autograd runs backward on its own thread
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches += n; }
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  set_error("CUDA error in %s: %s", what, cudaGetErrorString(e));
+  return B200GS_ERR_CUDA;
+}
+int debug_sync(const B200GSParams* prm, cudaStream_t s, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && prm->debug) e = cudaStreamSynchronize(s);
+  return check_cuda(e, what);
+}
+
+static int tile_bits_for(int num_tiles) {
+  int bits = 1;
+  while ((1 << bits) <= num_tiles) bits++;  // room for the invalid id == num_tiles
+  return bits;
+}
+
+static GeomBuf carve_geom(char* base, int P, size_t* bytes) {
+  Carver c(base);
+  GeomBuf g;
+  g.rec = c.take<float4>((size_t)P * REC_F4);
+  g.depth_key = c.take<uint32_t>(P);
+  g.idx = c.take<uint32_t>(P);
+  g.key_sorted = c.take<uint32_t>(P);
+  g.perm = c.take<uint32_t>(P);
+  g.tiles = c.take<uint32_t>(P);
+  g.offsets = c.take<uint32_t>(P);
+  g.clamped = c.take<uint8_t>(P);
+  g.cub_temp_bytes = depth_sort_temp_bytes(P);
+  g.cub_temp = c.take<char>(g.cub_temp_bytes);
+  if (bytes) *bytes = c.bytes();
+  return g;
+}
+
+static BinBuf carve_binning(char* base, int64_t D, int tile_bits, size_t* bytes) {
+  Carver c(base);
+  BinBuf b;
+  b.slab = c.take<float4>((size_t)D * REC_F4);
+  b.keys = c.take<uint32_t>(D);
+  b.vals = c.take<uint32_t>(D);
+  b.keys_sorted = c.take<uint32_t>(D);
+  b.vals_sorted = c.take<uint32_t>(D);
+  b.cub_temp_bytes = tile_sort_temp_bytes(D, tile_bits);
+  b.cub_temp = c.take<char>(b.cub_temp_bytes);
+  if (bytes) *bytes = c.bytes();
+  return b;
+}
+
+static ImgBuf carve_img(char* base, int H, int W, size_t* bytes) {
+  Carver c(base);
+  ImgBuf im;
+  const size_t tiles = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+  im.ranges = c.take<uint2>(tiles);
+  im.pix = c.take<float4>((size_t)H * W);
+  im.n_contrib = c.take<uint32_t>((size_t)H * W);
+  if (bytes) *bytes = c.bytes();
+  return im;
+}
+
+static int check_params(const B200GSParams* p) {
+  if (!p) { set_error("params is NULL"); return B200GS_ERR_INVALID_ARG; }
+  if (p->P < 0 || p->image_height <= 0 || p->image_width <= 0) {
+    set_error("invalid sizes P=%d H=%d W=%d", p->P, p->image_height, p->image_width);
+    return B200GS_ERR_INVALID_ARG;
+  }
+  if (p->sh_degree < 0 || p->sh_degree > 3) {
+    set_error("sh_degree must be 0..3, got %d", p->sh_degree);
+    return B200GS_ERR_INVALID_ARG;
+  }
+  if (!(p->tanfovx > 0.f) || !(p->tanfovy > 0.f)) {
+    set_error("tanfovx/tanfovy must be positive");
+    return B200GS_ERR_INVALID_ARG;
+  }
+  return 0;
+}
+
+static int check_inputs(const B200GSParams* p, const float* means3D, const float* shs,
+                        const float* colors_precomp, const float* opacities, const float* scales,
+                        const float* rotations, const float* cov3D_precomp) {
+  if (p->P == 0) return 0;
+  if (!means3D || !opacities) { set_error("means3D/opacities must not be NULL"); return B200GS_ERR_INVALID_ARG; }
+  if ((shs == nullptr) == (colors_precomp == nullptr)) {
+    set_error("provide exactly one of shs / colors_precomp");
+    return B200GS_ERR_INVALID_ARG;
+  }
+  const bool sr = scales != nullptr && rotations != nullptr;
+  if (sr == (cov3D_precomp != nullptr) || ((scales != nullptr) != (rotations != nullptr))) {
+    set_error("provide exactly one of (scales, rotations) / cov3D_precomp");
+    return B200GS_ERR_INVALID_ARG;
+  }
+  if (shs && p->M < (p->sh_degree + 1) * (p->sh_degree + 1)) {
+    set_error("shs holds M=%d coefficients, sh_degree=%d needs %d", p->M, p->sh_degree,
+              (p->sh_degree + 1) * (p->sh_degree + 1));
+    return B200GS_ERR_INVALID_ARG;
+  }
+  if (rotations && (reinterpret_cast<uintptr_t>(rotations) & 15)) {
+    set_error("rotations must be 16-byte aligned");
+    return B200GS_ERR_INVALID_ARG;
+  }
+  return 0;
+}
+
+static char* grow(B200GSAlloc a, size_t bytes, const char* what) {
+  if (!a.resize) { set_error("%s allocator is NULL", what); return nullptr; }
+  char* p = a.resize(a.ctx, bytes);
+  if (!p && bytes) set_error("%s allocator returned NULL for %zu bytes", what, bytes);
+  else if (reinterpret_cast<uintptr_t>(p) & 127) { set_error("%s buffer must be 128-byte aligned", what); return nullptr; }
+  return p;
+}
+
+}  // namespace b200gs
+
+using namespace b200gs;
+
+extern "C" {
+
+const char* b200gs_last_error(void) { return g_err; }
+int b200gs_version(void) { return B200GS_VERSION; }
+int64_t b200gs_launch_count(int reset) {
+  return reset ? g_launches.exchange(0) : g_launches.load();
+}
+
+int b200gs_buffer_sizes(int32_t P, int32_t H, int32_t W, int64_t D, size_t* geom_bytes,
+                        size_t* binning_bytes, size_t* img_bytes) {
+  if (P < 0 || H <= 0 || W <= 0 || D < 0) { set_error("invalid sizes"); return B200GS_ERR_INVALID_ARG; }
+  const int num_tiles = ((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+  if (geom_bytes) carve_geom(nullptr, P, geom_bytes);
+  if (binning_bytes) carve_binning(nullptr, D, tile_bits_for(num_tiles), binning_bytes);
+  if (img_bytes) carve_img(nullptr, H, W, img_bytes);
+  return 0;
+}
+
+int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewmatrix,
+                   const float* projmatrix, const float* campos, const float* means3D,
+                   const float* shs, const float* colors_precomp, const float* opacities,
+                   const float* scales, const float* rotations, const float* cov3D_precomp,
+                   float* out_color, int32_t* radii, B200GSAlloc geom, B200GSAlloc binning,
+                   B200GSAlloc img, int32_t* num_rendered, void* stream) {
+  g_err[0] = 0;
+  int rc;
+  if ((rc = check_params(prm))) return rc;
+  if ((rc = check_inputs(prm, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp))) return rc;
+  if (!bg || !viewmatrix || !projmatrix || !campos || !out_color || (prm->P && !radii) || !num_rendered) {
+    set_error("bg/viewmatrix/projmatrix/campos/out_color/radii/num_rendered must not be NULL");
+    return B200GS_ERR_INVALID_ARG;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int P = prm->P, H = prm->image_height, W = prm->image_width;
+  const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+  const int num_tiles = gx * gy;
+  const int tile_bits = tile_bits_for(num_tiles);
+
+  size_t geom_bytes, img_bytes;
+  carve_geom(nullptr, P, &geom_bytes);
+  carve_img(nullptr, H, W, &img_bytes);
+  char* geom_p = grow(geom, geom_bytes, "geom");
+  char* img_p = grow(img, img_bytes, "img");
+  if (!geom_p || !img_p) return B200GS_ERR_ALLOC;
+  GeomBuf gb = carve_geom(geom_p, P, nullptr);
+  ImgBuf ib = carve_img(img_p, H, W, nullptr);
+
+  ProjectArgs pa;
+  pa.P = P; pa.M = prm->M; pa.W = W; pa.H = H; pa.gx = gx; pa.gy = gy;
+  pa.sh_vec = (shs && (prm->M & 3) == 0 && (reinterpret_cast<uintptr_t>(shs) & 15) == 0) ? 1 : 0;
+  pa.tanfovx = prm->tanfovx; pa.tanfovy = prm->tanfovy; pa.scale_modifier = prm->scale_modifier;
+  pa.means = means3D; pa.scales = scales; pa.rots = rotations; pa.opac = opacities; pa.shs = shs;
+  pa.colors_precomp = colors_precomp; pa.cov3d_precomp = cov3D_precomp;
+  pa.view = viewmatrix; pa.proj = projmatrix; pa.campos = campos;
+  pa.radii = radii; pa.rec = gb.rec; pa.depth_key = gb.depth_key; pa.idx = gb.idx; pa.tiles = gb.tiles;
+  pa.clamped = gb.clamped;
+  launch_project(pa, shs ? prm->sh_degree : -1, st);
+  if ((rc = debug_sync(prm, st, "project"))) return rc;
+
+  if ((rc = sort_by_depth_and_scan(gb, P, st))) return rc;
+  if ((rc = debug_sync(prm, st, "depth sort + scan"))) return rc;
+
+  uint32_t D = 0;
+  if (P > 0) {
+    if ((rc = check_cuda(cudaMemcpyAsync(&D, gb.offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st),
+                         "read num_rendered")))
+      return rc;
+    if ((rc = check_cuda(cudaStreamSynchronize(st), "sync num_rendered"))) return rc;
+  }
+  *num_rendered = (int32_t)D;
+
+  size_t bin_bytes;
+  carve_binning(nullptr, D, tile_bits, &bin_bytes);
+  char* bin_p = grow(binning, bin_bytes, "binning");
+  if (!bin_p && bin_bytes) return B200GS_ERR_ALLOC;
+  BinBuf bb = carve_binning(bin_p, D, tile_bits, nullptr);
+
+  if ((rc = check_cuda(cudaMemsetAsync(ib.ranges, 0, sizeof(uint2) * (size_t)num_tiles, st), "clear ranges"))) return rc;
+  if (D > 0) {
+    EmitArgs ea;
+    ea.P = P; ea.gx = gx; ea.gy = gy; ea.invalid_tile = (uint32_t)num_tiles;
+    ea.perm = gb.perm; ea.tiles = gb.tiles; ea.offsets = gb.offsets; ea.rec = gb.rec; ea.radii = radii;
+    ea.keys = bb.keys; ea.vals = bb.vals;
+    launch_emit_pairs(ea, st);
+    if ((rc = debug_sync(prm, st, "emit pairs"))) return rc;
+    if ((rc = sort_by_tile(bb, D, tile_bits, st))) return rc;
+    if ((rc = debug_sync(prm, st, "tile sort"))) return rc;
+    GatherArgs ga;
+    ga.D = D; ga.num_tiles = (uint32_t)num_tiles; ga.keys_sorted = bb.keys_sorted; ga.vals_sorted = bb.vals_sorted;
+    ga.rec = gb.rec; ga.slab = bb.slab; ga.ranges = ib.ranges;
+    launch_gather_slab(ga, st);
+    if ((rc = debug_sync(prm, st, "gather slab"))) return rc;
+  }
+
+  RenderArgs ra;
+  ra.W = W; ra.H = H; ra.ranges = ib.ranges; ra.slab = bb.slab; ra.bg = bg; ra.out_color = out_color;
+  ra.pix = ib.pix; ra.n_contrib = ib.n_contrib;
+  launch_render(ra, st);
+  return debug_sync(prm, st, "render");
+}
+
+int b200gs_backward(const B200GSParams* prm, const float* bg, const float* viewmatrix,
+                    const float* projmatrix, const float* campos, const float* means3D,
+                    const float* shs, const float* colors_precomp, const float* opacities,
+                    const float* scales, const float* rotations, const float* cov3D_precomp,
+                    const int32_t* radii, const char* geom, const char* binning, const char* img,
+                    int32_t num_rendered, const float* dL_dout_color, float* dL_dmeans3D,
+                    float* dL_dmeans2D, float* dL_dshs, float* dL_dcolors_precomp,
+                    float* dL_dopacities, float* dL_dscales, float* dL_drotations,
+                    float* dL_dcov3D, B200GSAlloc scratch, void* stream) {
+  g_err[0] = 0;
+  int rc;
+  if ((rc = check_params(prm))) return rc;
+  if ((rc = check_inputs(prm, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp))) return rc;
+  const int P = prm->P, H = prm->image_height, W = prm->image_width;
+  if (P == 0) return 0;
+  if (!bg || !viewmatrix || !projmatrix || !campos || !radii || !geom || !img || !dL_dout_color ||
+      !dL_dmeans3D || !dL_dmeans2D || !dL_dopacities || (num_rendered > 0 && !binning)) {
+    set_error("backward: required pointer is NULL");
+    return B200GS_ERR_INVALID_ARG;
+  }
+  if ((shs && !dL_dshs) || (colors_precomp && !dL_dcolors_precomp) || (scales && (!dL_dscales || !dL_drotations)) ||
+      (cov3D_precomp && !dL_dcov3D)) {
+    set_error("backward: gradient output missing for a provided input");
+    return B200GS_ERR_INVALID_ARG;
+  }
+  if (dL_drotations && (reinterpret_cast<uintptr_t>(dL_drotations) & 15)) {
+    set_error("dL_drotations must be 16-byte aligned");
+    return B200GS_ERR_INVALID_ARG;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+  const int tile_bits = tile_bits_for(gx * gy);
+  GeomBuf gb = carve_geom(const_cast<char*>(geom), P, nullptr);
+  BinBuf bb = carve_binning(const_cast<char*>(binning), num_rendered, tile_bits, nullptr);
+  ImgBuf ib = carve_img(const_cast<char*>(img), H, W, nullptr);
+
+  const size_t g2_bytes = sizeof(float) * GRAD2D_STRIDE * (size_t)P;
+  char* g2_p = grow(scratch, g2_bytes, "scratch");
+  if (!g2_p) return B200GS_ERR_ALLOC;
+  float* grad2d = reinterpret_cast<float*>(g2_p);
+  if ((rc = check_cuda(cudaMemsetAsync(grad2d, 0, g2_bytes, st), "clear grad2d"))) return rc;
+
+  if (num_rendered > 0) {
+    RenderBwdArgs ra;
+    ra.W = W; ra.H = H; ra.ranges = ib.ranges; ra.slab = bb.slab; ra.bg = bg; ra.pix = ib.pix;
+    ra.n_contrib = ib.n_contrib; ra.dL_dpix = dL_dout_color; ra.grad2d = grad2d;
+    launch_render_bwd(ra, st);
+    if ((rc = debug_sync(prm, st, "render backward"))) return rc;
+  }
+
+  ProjectBwdArgs pa;
+  pa.P = P; pa.M = prm->M; pa.W = W; pa.H = H;
+  pa.sh_vec = (shs && (prm->M & 3) == 0 && (reinterpret_cast<uintptr_t>(shs) & 15) == 0 &&
+               (reinterpret_cast<uintptr_t>(dL_dshs) & 15) == 0) ? 1 : 0;
+  pa.tanfovx = prm->tanfovx; pa.tanfovy = prm->tanfovy; pa.scale_modifier = prm->scale_modifier;
+  pa.means = means3D; pa.scales = scales; pa.rots = rotations; pa.shs = shs; pa.cov3d_precomp = cov3D_precomp;
+  pa.view = viewmatrix; pa.proj = projmatrix; pa.campos = campos;
+  pa.radii = radii; pa.tiles = gb.tiles; pa.clamped = gb.clamped; pa.grad2d = grad2d;
+  pa.dL_dmeans = dL_dmeans3D; pa.dL_dmeans2D = dL_dmeans2D; pa.dL_dshs = dL_dshs; pa.dL_dcolors = dL_dcolors_precomp;
+  pa.dL_dopac = dL_dopacities; pa.dL_dscales = dL_dscales; pa.dL_drots = dL_drotations; pa.dL_dcov3D = dL_dcov3D;
+  launch_project_bwd(pa, shs ? prm->sh_degree : -1, st);
+  return debug_sync(prm, st, "project backward");
+}
+
+int b200gs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
+                        const float* projmatrix, uint8_t* present, void* stream) {
+  g_err[0] = 0;
+  (void)projmatrix;
+  if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) {
+    set_error("mark_visible: invalid arguments");
+    return B200GS_ERR_INVALID_ARG;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  launch_mark_visible(P, means3D, viewmatrix, present, st);
+  return check_cuda(cudaGetLastError(), "mark_visible");
+}
+
+}  // extern "C"

@@ -1,0 +1,113 @@
+// common.cuh -- shared device helpers, buffer carving and PTX wrappers for libb200gs (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/b200gs.h"
+
+namespace b200gs {
+
+constexpr int TILE = 16;            // tile edge in pixels (fixed: parity of the 3-sigma rect culling)
+constexpr int REC_F4 = 3;           // float4s per projected-splat record (48 B)
+constexpr int GRAD2D_STRIDE = 12;   // floats per Gaussian in the screen-space gradient accumulator
+
+// ---- projected-splat record (48 B, three float4) ----------------------------------------------
+//   q0 = { x, y, A, B }            pixel centre, conic
+//   q1 = { C, opacity, thr, idx }  thr = ln(255*opacity) + slack: 0.5*q <= thr  <=>  alpha >= 1/255
+//   q2 = { r, g, b, depth }
+// The same layout is used per Gaussian (geom buffer) and per (Gaussian,tile) pair in tile-sorted
+// order (binning buffer "slab"), so a tile's slab is one contiguous, 16-byte aligned byte range
+// that a single TMA bulk copy can fetch.
+
+// ---- buffer carving (128-byte aligned chunks inside caller-owned byte buffers) -----------------
+struct Carver {
+  char* p;
+  size_t off;
+  __host__ explicit Carver(char* base) : p(base), off(0) {}
+  template <typename T>
+  __host__ T* take(size_t count) {
+    off = (off + 127) & ~size_t(127);
+    T* r = p ? reinterpret_cast<T*>(p + off) : nullptr;
+    off += count * sizeof(T);
+    return r;
+  }
+  __host__ size_t bytes() const { return (off + 127) & ~size_t(127); }
+};
+
+struct GeomBuf {
+  float4* rec;          // [P*3]
+  uint32_t* depth_key;  // [P]
+  uint32_t* idx;        // [P] iota
+  uint32_t* key_sorted; // [P]
+  uint32_t* perm;       // [P] Gaussian indices in depth order
+  uint32_t* tiles;      // [P] tiles touched (tight count)
+  uint32_t* offsets;    // [P] inclusive scan of tiles[perm[i]]
+  uint8_t* clamped;     // [P] bit c set: colour channel c was clamped at 0
+  char* cub_temp;
+  size_t cub_temp_bytes;
+};
+
+struct BinBuf {
+  float4* slab;         // [D*3] records in (tile, depth) order
+  uint32_t* keys;       // [D] tile ids, emit order (depth-major)
+  uint32_t* vals;       // [D] Gaussian ids
+  uint32_t* keys_sorted;
+  uint32_t* vals_sorted;
+  char* cub_temp;
+  size_t cub_temp_bytes;
+};
+
+struct ImgBuf {
+  uint2* ranges;        // [tiles] [start,end) into the slab
+  float4* pix;          // [H*W] {accumulated r,g,b (no background), final transmittance}
+  uint32_t* n_contrib;  // [H*W] 1-based list position of the last contributor
+};
+
+// ---- small math helpers ---------------------------------------------------------------------
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(hi, fmaxf(lo, v)); }
+
+// ---- mbarrier / TMA (1-D bulk copy) PTX wrappers ---------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk async copy (TMA, SASS UBLKCP); bytes multiple of 16, both 16-B aligned.
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ---- launch accounting / error plumbing (host) -------------------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int check_cuda(cudaError_t e, const char* what);
+int debug_sync(const B200GSParams* prm, cudaStream_t s, const char* what);
+
+}  // namespace b200gs

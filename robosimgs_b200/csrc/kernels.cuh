@@ -1,0 +1,83 @@
+// kernels.cuh -- argument blocks and host launchers shared between the translation units.
+#pragma once
+#include "common.cuh"
+
+namespace b200gs {
+
+struct ProjectArgs {
+  int P, M, W, H, gx, gy, sh_vec;
+  float tanfovx, tanfovy, scale_modifier;
+  const float *means, *scales, *rots, *opac, *shs, *colors_precomp, *cov3d_precomp;
+  const float *view, *proj, *campos;
+  int32_t* radii;
+  float4* rec;
+  uint32_t *depth_key, *idx, *tiles;
+  uint8_t* clamped;
+};
+
+struct EmitArgs {
+  int P, gx, gy;
+  uint32_t invalid_tile;
+  const uint32_t *perm, *tiles, *offsets;
+  const float4* rec;
+  const int32_t* radii;
+  uint32_t *keys, *vals;
+};
+
+struct GatherArgs {
+  int64_t D;
+  uint32_t num_tiles;
+  const uint32_t *keys_sorted, *vals_sorted;
+  const float4* rec;
+  float4* slab;
+  uint2* ranges;
+};
+
+struct RenderArgs {
+  int W, H;
+  const uint2* ranges;
+  const float4* slab;
+  const float* bg;
+  float* out_color;     // [3][H][W]
+  float4* pix;          // [H*W]
+  uint32_t* n_contrib;  // [H*W]
+};
+
+struct RenderBwdArgs {
+  int W, H;
+  const uint2* ranges;
+  const float4* slab;
+  const float* bg;
+  const float4* pix;
+  const uint32_t* n_contrib;
+  const float* dL_dpix;  // [3][H][W]
+  float* grad2d;         // [P][12], zero-initialised
+};
+
+struct ProjectBwdArgs {
+  int P, M, W, H, sh_vec;
+  float tanfovx, tanfovy, scale_modifier;
+  const float *means, *scales, *rots, *shs, *cov3d_precomp;
+  const float *view, *proj, *campos;
+  const int32_t* radii;
+  const uint32_t* tiles;
+  const uint8_t* clamped;
+  const float* grad2d;
+  float *dL_dmeans, *dL_dmeans2D, *dL_dshs, *dL_dcolors, *dL_dopac, *dL_dscales, *dL_drots, *dL_dcov3D;
+};
+
+void launch_project(const ProjectArgs& a, int deg, cudaStream_t st);
+void launch_emit_pairs(const EmitArgs& a, cudaStream_t st);
+void launch_gather_slab(const GatherArgs& a, cudaStream_t st);
+void launch_mark_visible(int P, const float* means, const float* view, uint8_t* present, cudaStream_t st);
+void launch_project_bwd(const ProjectBwdArgs& a, int deg, cudaStream_t st);
+void launch_render(const RenderArgs& a, cudaStream_t st);
+void launch_render_bwd(const RenderBwdArgs& a, cudaStream_t st);
+
+// binning.cu (CUB): temp-storage sizing and the two sorts + scan
+size_t depth_sort_temp_bytes(int P);
+size_t tile_sort_temp_bytes(int64_t D, int tile_bits);
+int sort_by_depth_and_scan(const GeomBuf& g, int P, cudaStream_t st);
+int sort_by_tile(const BinBuf& b, int64_t D, int tile_bits, cudaStream_t st);
+
+}  // namespace b200gs

@@ -1,0 +1,691 @@
+// project.cu -- per-Gaussian kernels: projection + SH colour (forward), tile-pair emission,
+// fused projection/SH/covariance adjoint (backward), near-plane visibility.
+//
+// Replaces: a3 preprocessCUDA fwd, a5 duplicateWithKeys, a10 computeCov2DCUDA bwd,
+// a11 preprocessCUDA bwd, a12 checkFrustum -- of the public diff-gaussian-rasterization named by
+// BASELINE.json:north_star (third-party; the reference repo only delegates, README.md:75).
+// Arithmetic follows oracle/gs_oracle_impl.h step by step.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace b200gs {
+
+struct CamConst {
+  float v[16];
+  float p[16];
+  float cam[3];
+};
+
+__device__ __forceinline__ void load_cam(CamConst& c, const float* __restrict__ view,
+                                         const float* __restrict__ proj,
+                                         const float* __restrict__ campos) {
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    c.v[i] = __ldg(view + i);
+    c.p[i] = __ldg(proj + i);
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++) c.cam[i] = __ldg(campos + i);
+}
+
+// Sigma = R diag(mod*s)^2 R^T, 6 unique entries (xx,xy,xz,yy,yz,zz)
+__device__ __forceinline__ void cov3d_from_scale_rot(float3 s, float mod, float4 q, float* cov) {
+  const float r = q.x, x = q.y, y = q.z, z = q.w;
+  const float R00 = 1.f - 2.f * (y * y + z * z), R01 = 2.f * (x * y - r * z), R02 = 2.f * (x * z + r * y);
+  const float R10 = 2.f * (x * y + r * z), R11 = 1.f - 2.f * (x * x + z * z), R12 = 2.f * (y * z - r * x);
+  const float R20 = 2.f * (x * z - r * y), R21 = 2.f * (y * z + r * x), R22 = 1.f - 2.f * (x * x + y * y);
+  const float d0 = mod * s.x, d1 = mod * s.y, d2 = mod * s.z;
+  const float m00 = R00 * d0, m01 = R01 * d1, m02 = R02 * d2;
+  const float m10 = R10 * d0, m11 = R11 * d1, m12 = R12 * d2;
+  const float m20 = R20 * d0, m21 = R21 * d1, m22 = R22 * d2;
+  cov[0] = m00 * m00 + m01 * m01 + m02 * m02;
+  cov[1] = m00 * m10 + m01 * m11 + m02 * m12;
+  cov[2] = m00 * m20 + m01 * m21 + m02 * m22;
+  cov[3] = m10 * m10 + m11 * m11 + m12 * m12;
+  cov[4] = m10 * m20 + m11 * m21 + m12 * m22;
+  cov[5] = m20 * m20 + m21 * m21 + m22 * m22;
+}
+
+struct Ewa {
+  float t[3];       // view-space mean with the 1.3*tanfov clamp applied to x,y
+  float m[2][3];    // J * Wr
+  float xmask, ymask;
+  float fx, fy;
+};
+
+__device__ __forceinline__ void ewa_jacobian(const CamConst& c, float3 mu, float W, float H,
+                                             float tanfovx, float tanfovy, Ewa& e) {
+  float tx = c.v[0] * mu.x + c.v[4] * mu.y + c.v[8] * mu.z + c.v[12];
+  float ty = c.v[1] * mu.x + c.v[5] * mu.y + c.v[9] * mu.z + c.v[13];
+  const float tz = c.v[2] * mu.x + c.v[6] * mu.y + c.v[10] * mu.z + c.v[14];
+  const float limx = 1.3f * tanfovx, limy = 1.3f * tanfovy;
+  const float txtz = tx / tz, tytz = ty / tz;
+  e.xmask = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
+  e.ymask = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
+  tx = fminf(limx, fmaxf(-limx, txtz)) * tz;
+  ty = fminf(limy, fmaxf(-limy, tytz)) * tz;
+  e.t[0] = tx; e.t[1] = ty; e.t[2] = tz;
+  e.fx = W / (2.f * tanfovx);
+  e.fy = H / (2.f * tanfovy);
+  const float j00 = e.fx / tz, j02 = -(e.fx * tx) / (tz * tz);
+  const float j11 = e.fy / tz, j12 = -(e.fy * ty) / (tz * tz);
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    e.m[0][k] = j00 * c.v[4 * k + 0] + j02 * c.v[4 * k + 2];
+    e.m[1][k] = j11 * c.v[4 * k + 1] + j12 * c.v[4 * k + 2];
+  }
+}
+
+// Sigma2D = M Sigma M^T + 0.3 I  ->  (a,b,c)
+__device__ __forceinline__ void cov2d(const Ewa& e, const float* c3, float& a, float& b, float& c) {
+  float ms[2][3];
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    ms[r][0] = e.m[r][0] * c3[0] + e.m[r][1] * c3[1] + e.m[r][2] * c3[2];
+    ms[r][1] = e.m[r][0] * c3[1] + e.m[r][1] * c3[3] + e.m[r][2] * c3[4];
+    ms[r][2] = e.m[r][0] * c3[2] + e.m[r][1] * c3[4] + e.m[r][2] * c3[5];
+  }
+  a = ms[0][0] * e.m[0][0] + ms[0][1] * e.m[0][1] + ms[0][2] * e.m[0][2] + 0.3f;
+  b = ms[0][0] * e.m[1][0] + ms[0][1] * e.m[1][1] + ms[0][2] * e.m[1][2];
+  c = ms[1][0] * e.m[1][0] + ms[1][1] * e.m[1][1] + ms[1][2] * e.m[1][2] + 0.3f;
+}
+
+#define SH_C0 0.28209479177387814f
+#define SH_C1 0.4886025119029199f
+__device__ __constant__ float SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                          -1.0925484305920792f, 0.5462742152960396f};
+__device__ __constant__ float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f,  -0.4570457994644658f,
+                                          0.3731763325901154f,  -0.4570457994644658f, 1.445305721320277f,
+                                          -0.5900435899266435f};
+
+template <int DEG>
+__device__ __forceinline__ void sh_basis(float x, float y, float z, float* b) {
+  b[0] = SH_C0;
+  if (DEG > 0) {
+    b[1] = -SH_C1 * y; b[2] = SH_C1 * z; b[3] = -SH_C1 * x;
+  }
+  if (DEG > 1) {
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    b[4] = SH_C2[0] * xy;
+    b[5] = SH_C2[1] * yz;
+    b[6] = SH_C2[2] * (2.f * zz - xx - yy);
+    b[7] = SH_C2[3] * xz;
+    b[8] = SH_C2[4] * (xx - yy);
+    if (DEG > 2) {
+      b[9] = SH_C3[0] * y * (3.f * xx - yy);
+      b[10] = SH_C3[1] * xy * z;
+      b[11] = SH_C3[2] * y * (4.f * zz - xx - yy);
+      b[12] = SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+      b[13] = SH_C3[4] * x * (4.f * zz - xx - yy);
+      b[14] = SH_C3[5] * z * (xx - yy);
+      b[15] = SH_C3[6] * x * (xx - 3.f * yy);
+    }
+  }
+}
+
+// Load the first NF floats of a Gaussian's SH row.  Rows of M*3 floats are 16-byte aligned when
+// M % 4 == 0 (M = 16 for degree-3 storage): float4 path, one 128-bit load per 4 floats.
+template <int NF>
+__device__ __forceinline__ void load_sh_row(const float* __restrict__ row, bool vec_ok, float* f) {
+  if (vec_ok) {
+    constexpr int NV = (NF + 3) / 4;
+    const float4* r4 = reinterpret_cast<const float4*>(row);
+    float4 v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; i++) v[i] = __ldg(r4 + i);
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      if (4 * i + 0 < NF) f[4 * i + 0] = v[i].x;
+      if (4 * i + 1 < NF) f[4 * i + 1] = v[i].y;
+      if (4 * i + 2 < NF) f[4 * i + 2] = v[i].z;
+      if (4 * i + 3 < NF) f[4 * i + 3] = v[i].w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NF; i++) f[i] = __ldg(row + i);
+  }
+}
+
+// ---- tile coverage --------------------------------------------------------------------------------
+// The public algorithm assigns a Gaussian to every tile of the square [c - r, c + r] with
+// r = ceil(3 sqrt(lambda_max)).  A pixel only receives a contribution when alpha = o*exp(power)
+// >= 1/255, i.e. when 0.5*q(d) <= ln(255 o) with q the conic quadratic form.  Tiles of the square
+// that the ellipse {0.5 q <= thr} cannot reach contribute nothing to the image or to any gradient,
+// so they are dropped: coverage = reference rect  intersected with  per-tile-row ellipse spans.
+// thr carries a +0.01 slack (alpha ratio 1%) so fp32 rounding can only add pairs, never lose one.
+struct TileRect {
+  int x0, y0, x1, y1;  // [x0,x1) x [y0,y1) in tiles
+};
+
+__device__ __forceinline__ TileRect reference_rect(float px, float py, int radius, int gx, int gy) {
+  TileRect r;
+  const float fr = (float)radius;
+  r.x0 = min(gx, max(0, (int)((px - fr) / TILE)));
+  r.y0 = min(gy, max(0, (int)((py - fr) / TILE)));
+  r.x1 = min(gx, max(0, (int)((px + fr + (TILE - 1)) / TILE)));
+  r.y1 = min(gy, max(0, (int)((py + fr + (TILE - 1)) / TILE)));
+  return r;
+}
+
+struct SpanCtx {
+  float x, y, A, B, C;
+  float tau;        // 2*thr
+  float inv_A;
+  float det;        // A*C - B*B
+  float x_ext;      // half-extent of the ellipse in x
+  float y_at_xext;  // dy at the right-most point of the ellipse
+  float y_ext;
+};
+
+__device__ __forceinline__ bool span_setup(SpanCtx& s, float x, float y, float A, float B, float C,
+                                           float thr) {
+  s.x = x; s.y = y; s.A = A; s.B = B; s.C = C;
+  s.tau = __fmul_rn(2.f, thr);
+  s.det = __fmaf_rn(A, C, -__fmul_rn(B, B));
+  if (!(thr > 0.f) || !(s.det > 0.f) || !(A > 0.f) || !(C > 0.f)) return false;
+  s.inv_A = __frcp_rn(A);
+  s.x_ext = __fsqrt_rn(__fdiv_rn(__fmul_rn(s.tau, C), s.det));
+  s.y_ext = __fsqrt_rn(__fdiv_rn(__fmul_rn(s.tau, A), s.det));
+  s.y_at_xext = -__fdiv_rn(__fmul_rn(B, s.x_ext), C);
+  return true;
+}
+
+// x-interval (relative to the centre) of the ellipse {A dx^2 + 2B dx dy + C dy^2 <= tau} inside the
+// band dy in [a,b]; returns false if the band misses the ellipse.  1% outward padding on the
+// half-widths absorbs rounding.
+__device__ __noinline__ bool band_x_extent(const SpanCtx& s, float a, float b, float& lo, float& hi) {
+  a = fmaxf(a, -s.y_ext);
+  b = fminf(b, s.y_ext);
+  if (a > b) return false;
+  // half-width at dy: sqrt(A*tau - det*dy^2)/A ; centre line: -B*dy/A
+  const float da = __fsqrt_rn(fmaxf(0.f, __fmaf_rn(-s.det, __fmul_rn(a, a), __fmul_rn(s.A, s.tau))));
+  const float db = __fsqrt_rn(fmaxf(0.f, __fmaf_rn(-s.det, __fmul_rn(b, b), __fmul_rn(s.A, s.tau))));
+  const float ca = -__fmul_rn(s.B, a), cb = -__fmul_rn(s.B, b);
+  float xmax = fmaxf(__fmul_rn(__fadd_rn(ca, da), s.inv_A), __fmul_rn(__fadd_rn(cb, db), s.inv_A));
+  float xmin = fminf(__fmul_rn(__fadd_rn(ca, -da), s.inv_A), __fmul_rn(__fadd_rn(cb, -db), s.inv_A));
+  if (s.y_at_xext >= a && s.y_at_xext <= b) xmax = s.x_ext;     // right-most point inside the band
+  if (-s.y_at_xext >= a && -s.y_at_xext <= b) xmin = -s.x_ext;  // left-most point inside the band
+  const float pad = __fmaf_rn(0.01f, s.x_ext, 0.01f);
+  lo = xmin - pad;
+  hi = xmax + pad;
+  return true;
+}
+
+// tile-column span [c0,c1) of tile row ty, clipped to the reference rect
+__device__ __forceinline__ void row_span(const SpanCtx& s, const TileRect& r, int ty, int& c0, int& c1) {
+  // pixel-centre rows of this tile row: [16 ty, 16 ty + 15] (+- 0.01 px rounding pad)
+  const float a = (float)(ty * TILE) - 0.01f - s.y;
+  const float b = (float)(ty * TILE + TILE - 1) + 0.01f - s.y;
+  float lo, hi;
+  c0 = c1 = 0;
+  if (!band_x_extent(s, a, b, lo, hi)) return;
+  const float X0 = s.x + lo, X1 = s.x + hi;
+  // tile tx holds pixel centres [16 tx, 16 tx + 15]: intersects [X0,X1] iff 16tx <= X1 and 16tx+15 >= X0
+  int t0 = (int)ceilf((X0 - (float)(TILE - 1)) * (1.f / TILE));
+  int t1 = (int)floorf(X1 * (1.f / TILE)) + 1;
+  t0 = max(t0, r.x0);
+  t1 = min(t1, r.x1);
+  if (t1 > t0) { c0 = t0; c1 = t1; }
+}
+
+__device__ __forceinline__ uint32_t count_tiles(float x, float y, float A, float B, float C, float thr,
+                                                const TileRect& r) {
+  SpanCtx s;
+  if (!span_setup(s, x, y, A, B, C, thr)) return 0;
+  uint32_t n = 0;
+  for (int ty = r.y0; ty < r.y1; ty++) {
+    int c0, c1;
+    row_span(s, r, ty, c0, c1);
+    n += (uint32_t)(c1 - c0);
+  }
+  return n;
+}
+
+// ==================================================================================================
+// K1: projection + SH colour.  One thread per Gaussian.  DEG = -1: colours are precomputed.
+// ==================================================================================================
+template <int DEG>
+__global__ void __launch_bounds__(256) k_project(ProjectArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.P) return;
+  CamConst c;
+  load_cam(c, a.view, a.proj, a.campos);
+
+  a.idx[i] = (uint32_t)i;
+  uint32_t key = 0xFFFFFFFFu, ntiles = 0;
+  int radius = 0;
+
+  const float3 mu = make_float3(__ldg(a.means + 3 * i), __ldg(a.means + 3 * i + 1), __ldg(a.means + 3 * i + 2));
+  const float vz = c.v[2] * mu.x + c.v[6] * mu.y + c.v[10] * mu.z + c.v[14];
+  if (vz > 0.2f) {
+    const float hx = c.p[0] * mu.x + c.p[4] * mu.y + c.p[8] * mu.z + c.p[12];
+    const float hy = c.p[1] * mu.x + c.p[5] * mu.y + c.p[9] * mu.z + c.p[13];
+    const float hw = c.p[3] * mu.x + c.p[7] * mu.y + c.p[11] * mu.z + c.p[15];
+    const float pw = 1.f / (hw + 0.0000001f);
+    const float ndcx = hx * pw, ndcy = hy * pw;
+
+    float c3[6];
+    if (a.cov3d_precomp) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) c3[k] = __ldg(a.cov3d_precomp + 6 * (size_t)i + k);
+    } else {
+      const float3 s = make_float3(__ldg(a.scales + 3 * i), __ldg(a.scales + 3 * i + 1), __ldg(a.scales + 3 * i + 2));
+      const float4 q = __ldg(reinterpret_cast<const float4*>(a.rots) + i);
+      cov3d_from_scale_rot(s, a.scale_modifier, q, c3);
+    }
+    Ewa e;
+    ewa_jacobian(c, mu, (float)a.W, (float)a.H, a.tanfovx, a.tanfovy, e);
+    float ca, cb, cc;
+    cov2d(e, c3, ca, cb, cc);
+    const float det = ca * cc - cb * cb;
+    if (det != 0.f) {
+      const float det_inv = 1.f / det;
+      const float A = cc * det_inv, B = -cb * det_inv, C = ca * det_inv;
+      const float mid = 0.5f * (ca + cc);
+      const float disc = sqrtf(fmaxf(0.1f, mid * mid - det));
+      const float rad = ceilf(3.f * sqrtf(fmaxf(mid + disc, mid - disc)));
+      const float px = ((ndcx + 1.f) * a.W - 1.f) * 0.5f;
+      const float py = ((ndcy + 1.f) * a.H - 1.f) * 0.5f;
+      const int irad = (int)rad;
+      const TileRect r = reference_rect(px, py, irad, a.gx, a.gy);
+      if ((r.x1 - r.x0) * (r.y1 - r.y0) != 0) {
+        radius = irad;
+        const float o = __ldg(a.opac + i);
+        // 0.5*q <= thr  <=>  o*exp(-0.5 q) >= 1/255 ; slack keeps the test conservative
+        const float thr = __logf(255.f * o) + 0.01f;
+        ntiles = (o > 0.f) ? count_tiles(px, py, A, B, C, thr, r) : 0u;
+        if (ntiles > 0) {
+          float rgb[3];
+          uint32_t clampbits = 0;
+          if constexpr (DEG < 0) {
+            rgb[0] = __ldg(a.colors_precomp + 3 * (size_t)i);
+            rgb[1] = __ldg(a.colors_precomp + 3 * (size_t)i + 1);
+            rgb[2] = __ldg(a.colors_precomp + 3 * (size_t)i + 2);
+          } else {
+            constexpr int NB = (DEG < 0 ? 0 : (DEG + 1) * (DEG + 1));
+            constexpr int NF = NB * 3;
+            float f[NF > 0 ? NF : 1];
+            load_sh_row<NF>(a.shs + (size_t)i * a.M * 3, a.sh_vec != 0, f);
+            float dx = mu.x - c.cam[0], dy = mu.y - c.cam[1], dz = mu.z - c.cam[2];
+            const float inv = 1.f / sqrtf(dx * dx + dy * dy + dz * dz);
+            float b[NB > 0 ? NB : 1];
+            sh_basis<DEG>(dx * inv, dy * inv, dz * inv, b);
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+              float acc = 0.f;
+#pragma unroll
+              for (int k = 0; k < NB; k++) acc += b[k] * f[3 * k + ch];
+              acc += 0.5f;
+              if (acc < 0.f) clampbits |= (1u << ch);
+              rgb[ch] = fmaxf(acc, 0.f);
+            }
+          }
+          a.clamped[i] = (uint8_t)clampbits;
+          key = __float_as_uint(vz);
+          float4* rec = a.rec + (size_t)i * REC_F4;
+          rec[0] = make_float4(px, py, A, B);
+          rec[1] = make_float4(C, o, thr, __uint_as_float((uint32_t)i));
+          rec[2] = make_float4(rgb[0], rgb[1], rgb[2], vz);
+        }
+      }
+    }
+  }
+  a.radii[i] = radius;
+  a.depth_key[i] = key;
+  a.tiles[i] = ntiles;
+}
+
+// ==================================================================================================
+// K3: emit (tile id, Gaussian id) pairs in depth order.  Thread r handles the r-th nearest Gaussian;
+// offsets[] is the inclusive scan of the per-Gaussian tile counts in that order, so the pair list is
+// depth-major and a stable sort on the tile id alone yields the (tile, depth) order of the public
+// algorithm's 64-bit key sort.
+// ==================================================================================================
+__global__ void __launch_bounds__(256) k_emit_pairs(EmitArgs a) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= a.P) return;
+  const uint32_t g = a.perm[r];
+  const uint32_t n = a.tiles[g];
+  if (n == 0) return;
+  uint32_t off = a.offsets[r] - n;
+  const uint32_t end = off + n;
+  const float4 q0 = a.rec[(size_t)g * REC_F4], q1 = a.rec[(size_t)g * REC_F4 + 1];
+  const TileRect rect = reference_rect(q0.x, q0.y, a.radii[g], a.gx, a.gy);
+  SpanCtx s;
+  if (span_setup(s, q0.x, q0.y, q0.z, q0.w, q1.x, q1.z)) {
+    for (int ty = rect.y0; ty < rect.y1; ty++) {
+      int c0, c1;
+      row_span(s, rect, ty, c0, c1);
+      for (int tx = c0; tx < c1 && off < end; tx++) {
+        a.keys[off] = (uint32_t)(ty * a.gx + tx);
+        a.vals[off] = g;
+        off++;
+      }
+    }
+  }
+  // defensive: never leave unwritten slots (cannot happen; count and emit share band_x_extent)
+  for (; off < end; off++) {
+    a.keys[off] = a.invalid_tile;
+    a.vals[off] = g;
+  }
+}
+
+// ==================================================================================================
+// K5 + slab gather: per sorted pair, copy the 48-byte record into tile order and mark tile ranges.
+// ==================================================================================================
+__global__ void __launch_bounds__(256) k_gather_slab(GatherArgs a) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= a.D) return;
+  const uint32_t t = a.keys_sorted[j];
+  const uint32_t g = a.vals_sorted[j];
+  const float4* src = a.rec + (size_t)g * REC_F4;
+  const float4 q0 = __ldg(src), q1 = __ldg(src + 1), q2 = __ldg(src + 2);
+  float4* dst = a.slab + (size_t)j * REC_F4;
+  dst[0] = q0; dst[1] = q1; dst[2] = q2;
+  if (t < a.num_tiles) {
+    if (j == 0 || a.keys_sorted[j - 1] != t) a.ranges[t].x = (uint32_t)j;
+    if (j == a.D - 1 || a.keys_sorted[j + 1] != t) a.ranges[t].y = (uint32_t)(j + 1);
+  }
+}
+
+// ==================================================================================================
+// K10: near-plane visibility
+// ==================================================================================================
+__global__ void k_mark_visible(int P, const float* __restrict__ means, const float* __restrict__ view,
+                               uint8_t* __restrict__ present) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const float vz = __ldg(view + 2) * means[3 * i] + __ldg(view + 6) * means[3 * i + 1] +
+                   __ldg(view + 10) * means[3 * i + 2] + __ldg(view + 14);
+  present[i] = vz > 0.2f ? 1 : 0;
+}
+
+// ==================================================================================================
+// K8 + K9 fused: adjoint of the projection, SH colour and Sigma3D for one Gaussian per thread.
+// Reads the screen-space accumulator grad2d[P][12] = {dcol r,g,b, dopacity, dmean2D x,y (NDC-scaled),
+// dA, dB, dC, -, -, -} written by the compositing adjoint.  Every output element is written.
+// ==================================================================================================
+template <int DEG>
+__global__ void __launch_bounds__(256) k_project_bwd(ProjectBwdArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.P) return;
+  constexpr int NB = (DEG < 0 ? 0 : (DEG + 1) * (DEG + 1));
+
+  float gm[3] = {0.f, 0.f, 0.f};
+  float gcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float gs[3] = {0.f, 0.f, 0.f};
+  float gq[4] = {0.f, 0.f, 0.f, 0.f};
+  float g2x = 0.f, g2y = 0.f, gop = 0.f;
+  float gcol[3] = {0.f, 0.f, 0.f};
+  const bool active = a.radii[i] > 0 && a.tiles[i] > 0;
+  const bool vec_ok = a.sh_vec != 0;
+
+  if (active) {
+    CamConst c;
+    load_cam(c, a.view, a.proj, a.campos);
+    const float4* g4 = reinterpret_cast<const float4*>(a.grad2d + (size_t)i * GRAD2D_STRIDE);
+    const float4 ga4 = g4[0], gb4 = g4[1], gc4 = g4[2];
+    gcol[0] = ga4.x; gcol[1] = ga4.y; gcol[2] = ga4.z;
+    gop = ga4.w;
+    g2x = gb4.x; g2y = gb4.y;
+    const float gA = gb4.z, gB = gb4.w, gC = gc4.x;
+
+    const float3 mu = make_float3(__ldg(a.means + 3 * i), __ldg(a.means + 3 * i + 1), __ldg(a.means + 3 * i + 2));
+    float c3[6];
+    float3 s = make_float3(0.f, 0.f, 0.f);
+    float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
+    if (a.cov3d_precomp) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) c3[k] = __ldg(a.cov3d_precomp + 6 * (size_t)i + k);
+    } else {
+      s = make_float3(__ldg(a.scales + 3 * i), __ldg(a.scales + 3 * i + 1), __ldg(a.scales + 3 * i + 2));
+      q = __ldg(reinterpret_cast<const float4*>(a.rots) + i);
+      cov3d_from_scale_rot(s, a.scale_modifier, q, c3);
+    }
+    // ---- conic -> Sigma2D -> Sigma3D, view-space mean (oracle A.2) ----
+    Ewa e;
+    ewa_jacobian(c, mu, (float)a.W, (float)a.H, a.tanfovx, a.tanfovy, e);
+    float a_, b_, c_;
+    cov2d(e, c3, a_, b_, c_);
+    const float det = a_ * c_ - b_ * b_;
+    const float d2inv = 1.f / (det * det + 0.0000001f);
+    const float ga = d2inv * (-c_ * c_ * gA + b_ * c_ * gB + (det - a_ * c_) * gC);
+    const float gc = d2inv * (-a_ * a_ * gC + a_ * b_ * gB + (det - a_ * c_) * gA);
+    const float gb = d2inv * (2.f * b_ * c_ * gA - (det + 2.f * b_ * b_) * gB + 2.f * a_ * b_ * gC);
+    const float G2[2][2] = {{ga, 0.5f * gb}, {0.5f * gb, gc}};
+    float G2M[2][3];
+#pragma unroll
+    for (int r = 0; r < 2; r++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) G2M[r][k] = G2[r][0] * e.m[0][k] + G2[r][1] * e.m[1][k];
+    float GS[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) GS[r][k] = e.m[0][r] * G2M[0][k] + e.m[1][r] * G2M[1][k];
+    gcov[0] = GS[0][0]; gcov[3] = GS[1][1]; gcov[5] = GS[2][2];
+    gcov[1] = 2.f * GS[0][1]; gcov[2] = 2.f * GS[0][2]; gcov[4] = 2.f * GS[1][2];
+    const float S[3][3] = {{c3[0], c3[1], c3[2]}, {c3[1], c3[3], c3[4]}, {c3[2], c3[4], c3[5]}};
+    float gM[2][3];
+#pragma unroll
+    for (int r = 0; r < 2; r++)
+#pragma unroll
+      for (int k = 0; k < 3; k++)
+        gM[r][k] = 2.f * (G2M[r][0] * S[0][k] + G2M[r][1] * S[1][k] + G2M[r][2] * S[2][k]);
+    float gJ[2][3];
+#pragma unroll
+    for (int r = 0; r < 2; r++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) gJ[r][j] = gM[r][0] * c.v[j] + gM[r][1] * c.v[4 + j] + gM[r][2] * c.v[8 + j];
+    const float tz = 1.f / e.t[2], tz2 = tz * tz, tz3 = tz2 * tz;
+    const float gtx = e.xmask * (-e.fx * tz2 * gJ[0][2]);
+    const float gty = e.ymask * (-e.fy * tz2 * gJ[1][2]);
+    const float gtz = -e.fx * tz2 * gJ[0][0] - e.fy * tz2 * gJ[1][1] + (2.f * e.fx * e.t[0]) * tz3 * gJ[0][2] +
+                      (2.f * e.fy * e.t[1]) * tz3 * gJ[1][2];
+#pragma unroll
+    for (int k = 0; k < 3; k++) gm[k] += c.v[4 * k] * gtx + c.v[4 * k + 1] * gty + c.v[4 * k + 2] * gtz;
+
+    // ---- pixel centre through the full projection (oracle A.3) ----
+    const float hx = c.p[0] * mu.x + c.p[4] * mu.y + c.p[8] * mu.z + c.p[12];
+    const float hy = c.p[1] * mu.x + c.p[5] * mu.y + c.p[9] * mu.z + c.p[13];
+    const float hw = c.p[3] * mu.x + c.p[7] * mu.y + c.p[11] * mu.z + c.p[15];
+    const float w = 1.f / (hw + 0.0000001f);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const float dnx = c.p[4 * k] * w - c.p[4 * k + 3] * hx * w * w;
+      const float dny = c.p[4 * k + 1] * w - c.p[4 * k + 3] * hy * w * w;
+      gm[k] += dnx * g2x + dny * g2y;
+    }
+
+    // ---- SH colour (oracle A.4) ----
+    if constexpr (DEG >= 0) {
+      constexpr int NF = NB * 3;
+      float f[NF > 0 ? NF : 1];
+      load_sh_row<NF>(a.shs + (size_t)i * a.M * 3, vec_ok, f);
+      const float dx = mu.x - c.cam[0], dy = mu.y - c.cam[1], dz = mu.z - c.cam[2];
+      const float inv = 1.f / sqrtf(dx * dx + dy * dy + dz * dz);
+      const float x = dx * inv, y = dy * inv, z = dz * inv;
+      float b[NB > 0 ? NB : 1];
+      sh_basis<DEG>(x, y, z, b);
+      const uint32_t cl = a.clamped[i];
+      float gc3[3];
+#pragma unroll
+      for (int ch = 0; ch < 3; ch++) gc3[ch] = ((cl >> ch) & 1u) ? 0.f : gcol[ch];
+      // t_k = sum_ch sh[k][ch] * dL/drgb[ch]
+      float t[NB > 0 ? NB : 1];
+#pragma unroll
+      for (int k = 0; k < NB; k++) t[k] = f[3 * k] * gc3[0] + f[3 * k + 1] * gc3[1] + f[3 * k + 2] * gc3[2];
+      float gdx = 0.f, gdy = 0.f, gdz = 0.f;
+      if (DEG > 0) {
+        gdy += -SH_C1 * t[1]; gdz += SH_C1 * t[2]; gdx += -SH_C1 * t[3];
+      }
+      if (DEG > 1) {
+        const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+        gdx += SH_C2[0] * y * t[4];                 gdy += SH_C2[0] * x * t[4];
+        gdy += SH_C2[1] * z * t[5];                 gdz += SH_C2[1] * y * t[5];
+        gdx += SH_C2[2] * -2.f * x * t[6];          gdy += SH_C2[2] * -2.f * y * t[6];
+        gdz += SH_C2[2] * 4.f * z * t[6];
+        gdx += SH_C2[3] * z * t[7];                 gdz += SH_C2[3] * x * t[7];
+        gdx += SH_C2[4] * 2.f * x * t[8];           gdy += SH_C2[4] * -2.f * y * t[8];
+        if (DEG > 2) {
+          gdx += SH_C3[0] * 6.f * xy * t[9];        gdy += SH_C3[0] * (3.f * xx - 3.f * yy) * t[9];
+          gdx += SH_C3[1] * yz * t[10];             gdy += SH_C3[1] * xz * t[10];
+          gdz += SH_C3[1] * xy * t[10];
+          gdx += SH_C3[2] * -2.f * xy * t[11];      gdy += SH_C3[2] * (4.f * zz - xx - 3.f * yy) * t[11];
+          gdz += SH_C3[2] * 8.f * yz * t[11];
+          gdx += SH_C3[3] * -6.f * xz * t[12];      gdy += SH_C3[3] * -6.f * yz * t[12];
+          gdz += SH_C3[3] * (6.f * zz - 3.f * xx - 3.f * yy) * t[12];
+          gdx += SH_C3[4] * (4.f * zz - 3.f * xx - yy) * t[13];
+          gdy += SH_C3[4] * -2.f * xy * t[13];      gdz += SH_C3[4] * 8.f * xz * t[13];
+          gdx += SH_C3[5] * 2.f * xz * t[14];       gdy += SH_C3[5] * -2.f * yz * t[14];
+          gdz += SH_C3[5] * (xx - yy) * t[14];
+          gdx += SH_C3[6] * (3.f * xx - 3.f * yy) * t[15];
+          gdy += SH_C3[6] * -6.f * xy * t[15];
+        }
+      }
+      const float dot = x * gdx + y * gdy + z * gdz;
+      gm[0] += (gdx - x * dot) * inv;
+      gm[1] += (gdy - y * dot) * inv;
+      gm[2] += (gdz - z * dot) * inv;
+      // dL/dsh[k][ch] = basis_k * dL/drgb[ch]; reuse f[] as the output row
+#pragma unroll
+      for (int k = 0; k < NB; k++) {
+        f[3 * k] = b[k] * gc3[0]; f[3 * k + 1] = b[k] * gc3[1]; f[3 * k + 2] = b[k] * gc3[2];
+      }
+      float* row = a.dL_dshs + (size_t)i * a.M * 3;
+      const int total = a.M * 3;
+      if (vec_ok) {
+        float4* r4 = reinterpret_cast<float4*>(row);
+        constexpr int NV = (NF + 3) / 4;
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+          float4 o;
+          o.x = (4 * v + 0 < NF) ? f[(4 * v + 0 < NF) ? 4 * v + 0 : 0] : 0.f;
+          o.y = (4 * v + 1 < NF) ? f[(4 * v + 1 < NF) ? 4 * v + 1 : 0] : 0.f;
+          o.z = (4 * v + 2 < NF) ? f[(4 * v + 2 < NF) ? 4 * v + 2 : 0] : 0.f;
+          o.w = (4 * v + 3 < NF) ? f[(4 * v + 3 < NF) ? 4 * v + 3 : 0] : 0.f;
+          r4[v] = o;
+        }
+        for (int v = NV; v < total / 4; v++) r4[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+#pragma unroll
+        for (int k = 0; k < NF; k++) row[k] = f[k];
+        for (int k = NF; k < total; k++) row[k] = 0.f;
+      }
+    }
+
+    // ---- Sigma3D -> scale, quaternion (oracle A.5) ----
+    if (!a.cov3d_precomp) {
+      const float r = q.x, qx = q.y, qy = q.z, qz = q.w;
+      const float R[3][3] = {
+          {1.f - 2.f * (qy * qy + qz * qz), 2.f * (qx * qy - r * qz), 2.f * (qx * qz + r * qy)},
+          {2.f * (qx * qy + r * qz), 1.f - 2.f * (qx * qx + qz * qz), 2.f * (qy * qz - r * qx)},
+          {2.f * (qx * qz - r * qy), 2.f * (qy * qz + r * qx), 1.f - 2.f * (qx * qx + qy * qy)}};
+      const float mod = a.scale_modifier;
+      const float d[3] = {mod * s.x, mod * s.y, mod * s.z};
+      const float Gf[3][3] = {{gcov[0], 0.5f * gcov[1], 0.5f * gcov[2]},
+                              {0.5f * gcov[1], gcov[3], 0.5f * gcov[4]},
+                              {0.5f * gcov[2], 0.5f * gcov[4], gcov[5]}};
+      float F[3][3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        float acc = 0.f;
+#pragma unroll
+        for (int r_ = 0; r_ < 3; r_++) {
+          const float gmx = 2.f * (Gf[r_][0] * R[0][k] + Gf[r_][1] * R[1][k] + Gf[r_][2] * R[2][k]) * d[k];
+          acc += gmx * R[r_][k];
+          F[r_][k] = gmx * d[k];
+        }
+        gs[k] = mod * acc;
+      }
+      gq[0] = 2.f * (-qz * F[0][1] + qy * F[0][2] + qz * F[1][0] - qx * F[1][2] - qy * F[2][0] + qx * F[2][1]);
+      gq[1] = 2.f * (qy * F[0][1] + qz * F[0][2] + qy * F[1][0] - 2.f * qx * F[1][1] - r * F[1][2] +
+                     qz * F[2][0] + r * F[2][1] - 2.f * qx * F[2][2]);
+      gq[2] = 2.f * (-2.f * qy * F[0][0] + qx * F[0][1] + r * F[0][2] + qx * F[1][0] + qz * F[1][2] -
+                     r * F[2][0] + qz * F[2][1] - 2.f * qy * F[2][2]);
+      gq[3] = 2.f * (-2.f * qz * F[0][0] - r * F[0][1] + qx * F[0][2] + r * F[1][0] - 2.f * qz * F[1][1] +
+                     qy * F[1][2] + qx * F[2][0] + qy * F[2][1]);
+    }
+  } else if constexpr (DEG >= 0) {
+    // culled Gaussian: zero SH gradient row
+    float* row = a.dL_dshs + (size_t)i * a.M * 3;
+    const int total = a.M * 3;
+    if (vec_ok) {
+      float4* r4 = reinterpret_cast<float4*>(row);
+      for (int v = 0; v < total / 4; v++) r4[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      for (int k = 0; k < total; k++) row[k] = 0.f;
+    }
+  }
+
+  a.dL_dmeans[3 * (size_t)i] = gm[0];
+  a.dL_dmeans[3 * (size_t)i + 1] = gm[1];
+  a.dL_dmeans[3 * (size_t)i + 2] = gm[2];
+  a.dL_dmeans2D[3 * (size_t)i] = g2x;
+  a.dL_dmeans2D[3 * (size_t)i + 1] = g2y;
+  a.dL_dmeans2D[3 * (size_t)i + 2] = 0.f;
+  a.dL_dopac[i] = gop;
+  if (DEG < 0 && a.dL_dcolors) {
+    a.dL_dcolors[3 * (size_t)i] = gcol[0];
+    a.dL_dcolors[3 * (size_t)i + 1] = gcol[1];
+    a.dL_dcolors[3 * (size_t)i + 2] = gcol[2];
+  }
+  if (a.cov3d_precomp) {
+    if (a.dL_dcov3D) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) a.dL_dcov3D[6 * (size_t)i + k] = gcov[k];
+    }
+  } else {
+    a.dL_dscales[3 * (size_t)i] = gs[0];
+    a.dL_dscales[3 * (size_t)i + 1] = gs[1];
+    a.dL_dscales[3 * (size_t)i + 2] = gs[2];
+    reinterpret_cast<float4*>(a.dL_drots)[i] = make_float4(gq[0], gq[1], gq[2], gq[3]);
+  }
+}
+
+// ---- host launchers ------------------------------------------------------------------------------
+void launch_project(const ProjectArgs& a, int deg, cudaStream_t st) {
+  if (a.P == 0) return;
+  const dim3 grid((a.P + 255) / 256), block(256);
+  switch (deg) {
+    case -1: k_project<-1><<<grid, block, 0, st>>>(a); break;
+    case 0: k_project<0><<<grid, block, 0, st>>>(a); break;
+    case 1: k_project<1><<<grid, block, 0, st>>>(a); break;
+    case 2: k_project<2><<<grid, block, 0, st>>>(a); break;
+    default: k_project<3><<<grid, block, 0, st>>>(a); break;
+  }
+  count_launch();
+}
+
+void launch_emit_pairs(const EmitArgs& a, cudaStream_t st) {
+  if (a.P == 0) return;
+  k_emit_pairs<<<(a.P + 255) / 256, 256, 0, st>>>(a);
+  count_launch();
+}
+
+void launch_gather_slab(const GatherArgs& a, cudaStream_t st) {
+  if (a.D == 0) return;
+  k_gather_slab<<<(unsigned)((a.D + 255) / 256), 256, 0, st>>>(a);
+  count_launch();
+}
+
+void launch_mark_visible(int P, const float* means, const float* view, uint8_t* present, cudaStream_t st) {
+  if (P == 0) return;
+  k_mark_visible<<<(P + 255) / 256, 256, 0, st>>>(P, means, view, present);
+  count_launch();
+}
+
+void launch_project_bwd(const ProjectBwdArgs& a, int deg, cudaStream_t st) {
+  if (a.P == 0) return;
+  const dim3 grid((a.P + 255) / 256), block(256);
+  switch (deg) {
+    case -1: k_project_bwd<-1><<<grid, block, 0, st>>>(a); break;
+    case 0: k_project_bwd<0><<<grid, block, 0, st>>>(a); break;
+    case 1: k_project_bwd<1><<<grid, block, 0, st>>>(a); break;
+    case 2: k_project_bwd<2><<<grid, block, 0, st>>>(a); break;
+    default: k_project_bwd<3><<<grid, block, 0, st>>>(a); break;
+  }
+  count_launch();
+}
+
+}  // namespace b200gs

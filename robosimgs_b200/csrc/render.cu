@@ -1,0 +1,311 @@
+// render.cu -- per-tile front-to-back alpha compositing and its adjoint.
+//
+// Replaces rows a8 renderCUDA fwd and a9 renderCUDA bwd of the public
+// diff-gaussian-rasterization named by BASELINE.json:north_star (third-party; the reference repo
+// only delegates, /root/reference/README.md:75).  Per-pixel arithmetic follows
+// oracle/gs_oracle_impl.h gso_render / gso_render_backward.
+//
+// B200 design:
+//  * one CTA per 16x16 tile, 8 warps, each warp owns an 8x4 pixel block;
+//  * the tile's splat records are one contiguous 48-byte-record slab in HBM; chunks of 256 records
+//    are fetched with 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP) into a 2-stage shared-memory
+//    ring signalled through mbarriers -- no thread spends registers or issue slots on the fetch;
+//  * hierarchical culling: 32 lanes test 32 different records against the warp's 8x4 pixel block
+//    (exact minimum of the conic form over the block), one ballot, and only the surviving records
+//    are evaluated per pixel -- records are read from shared memory as 128-bit broadcasts;
+//  * early-out: per-warp vote when all 32 pixels are saturated, per-CTA __syncthreads_count;
+//  * adjoint: gradients of a record are reduced over the warp with a transposing butterfly
+//    (14 shuffles for 9 values) and leave the SM as one 9-lane RED.ADD.F32 to a 48-byte aligned
+//    accumulator row per Gaussian.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace b200gs {
+
+constexpr int CH = 256;      // records per ring stage
+constexpr int STAGES = 2;
+constexpr int CH_BYTES = CH * REC_F4 * 16;
+
+// Upper bound of `power` over the pixel block [x0,x1]x[y0,y1] is -0.5*qmin with qmin the minimum of
+// q(d) = A dx^2 + 2 B dx dy + C dy^2.  q is convex, so if the centre is outside the block the
+// minimum lies on an edge facing the centre; both facing edges are minimised in closed form.
+__device__ __forceinline__ bool block_may_contribute(float x, float y, float A, float B, float C, float thr,
+                                                     float x0, float y0, float x1, float y1) {
+  const float cx = clampf(x, x0, x1), cy = clampf(y, y0, y1);
+  const float dxe = cx - x, dye = cy - y;
+  // vertical edge X = cx: minimise over Y
+  float dy1 = clampf(y - B * dxe / C, y0, y1) - y;
+  const float q1 = A * dxe * dxe + 2.f * B * dxe * dy1 + C * dy1 * dy1;
+  // horizontal edge Y = cy: minimise over X
+  float dx2 = clampf(x - B * dye / A, x0, x1) - x;
+  const float q2 = A * dx2 * dx2 + 2.f * B * dx2 * dye + C * dye * dye;
+  const float q = fminf(q1, q2);
+  // rounding guard: relative to the magnitude of the cancelling terms
+  const float mag = fabsf(A) * (dxe * dxe + dx2 * dx2) + fabsf(C) * (dye * dye + dy1 * dy1);
+  return 0.5f * q - 4e-6f * mag <= thr;
+}
+
+struct RingState {
+  uint32_t n;        // records in this tile
+  uint32_t nchunks;
+};
+
+__device__ __forceinline__ void issue_chunk(const float4* slab, uint32_t start, uint32_t n, uint32_t c,
+                                            float4* stage, uint64_t* bar) {
+  const uint32_t cnt = min((uint32_t)CH, n - c * CH);
+  const uint32_t bytes = cnt * REC_F4 * 16;
+  mbar_expect_tx(bar, bytes);
+  tma_load_1d(stage, slab + (size_t)(start + c * CH) * REC_F4, bytes, bar);
+}
+
+// ==================================================================================================
+// K6: forward compositing
+// ==================================================================================================
+__global__ void __launch_bounds__(256) k_render_fwd(RenderArgs a) {
+  __shared__ __align__(128) float4 sm[STAGES][CH * REC_F4];
+  __shared__ __align__(8) uint64_t full[STAGES];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint2 range = a.ranges[blockIdx.y * gridDim.x + blockIdx.x];
+  const uint32_t n = range.y - range.x;
+  const uint32_t nchunks = (n + CH - 1) / CH;
+
+  const int bx = blockIdx.x * TILE + (warp & 1) * 8, by = blockIdx.y * TILE + (warp >> 1) * 4;
+  const int px = bx + (lane & 7), py = by + (lane >> 3);
+  const bool inside = px < a.W && py < a.H;
+  const float pxf = (float)px, pyf = (float)py;
+  const float rx0 = (float)bx, ry0 = (float)by;
+  const float rx1 = (float)min(bx + 7, a.W - 1), ry1 = (float)min(by + 3, a.H - 1);
+
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (nchunks > 0) issue_chunk(a.slab, range.x, n, 0, sm[0], &full[0]);
+    if (nchunks > 1) issue_chunk(a.slab, range.x, n, 1, sm[1], &full[1]);
+  }
+
+  bool done = !inside;
+  float T = 1.f, Cr = 0.f, Cg = 0.f, Cb = 0.f;
+  uint32_t last = 0;
+
+  for (uint32_t c = 0; c < nchunks; c++) {
+    const int s = c & 1;
+    mbar_wait(&full[s], (c >> 1) & 1);
+    const uint32_t cnt = min((uint32_t)CH, n - c * CH);
+    const float4* st = sm[s];
+    for (uint32_t base = 0; base < cnt; base += 32) {
+      if (__all_sync(0xffffffffu, done)) break;
+      const uint32_t j = base + lane;
+      bool hit = false;
+      if (j < cnt) {
+        const float4 q0 = st[j * REC_F4], q1 = st[j * REC_F4 + 1];
+        hit = block_may_contribute(q0.x, q0.y, q0.z, q0.w, q1.x, q1.z, rx0, ry0, rx1, ry1);
+      }
+      uint32_t mask = __ballot_sync(0xffffffffu, hit);
+      while (mask) {
+        const int b = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const uint32_t jj = base + b;
+        const float4 q0 = st[jj * REC_F4], q1 = st[jj * REC_F4 + 1], q2 = st[jj * REC_F4 + 2];
+        const float dx = q0.x - pxf, dy = q0.y - pyf;
+        const float power = -0.5f * (q0.z * dx * dx + q1.x * dy * dy) - q0.w * dx * dy;
+        const float alpha = fminf(0.99f, q1.y * __expf(power));
+        if (!done && power <= 0.f && alpha >= (1.f / 255.f)) {
+          const float test_T = T * (1.f - alpha);
+          if (test_T < 0.0001f) {
+            done = true;
+          } else {
+            const float w = alpha * T;
+            Cr = __fmaf_rn(q2.x, w, Cr);
+            Cg = __fmaf_rn(q2.y, w, Cg);
+            Cb = __fmaf_rn(q2.z, w, Cb);
+            T = test_T;
+            last = c * CH + jj + 1;
+          }
+        }
+      }
+    }
+    const int num_done = __syncthreads_count(done);
+    if (num_done == 256) {
+      // a prefetched chunk may still be in flight into our shared memory: drain before exit
+      if (tid == 0 && c + 1 < nchunks) mbar_wait(&full[(c + 1) & 1], ((c + 1) >> 1) & 1);
+      break;
+    }
+    if (tid == 0 && c + 2 < nchunks) issue_chunk(a.slab, range.x, n, c + 2, sm[s], &full[s]);
+  }
+
+  if (inside) {
+    const size_t pid = (size_t)py * a.W + px;
+    const size_t hw = (size_t)a.H * a.W;
+    a.pix[pid] = make_float4(Cr, Cg, Cb, T);
+    a.n_contrib[pid] = last;
+    a.out_color[pid] = __fmaf_rn(T, __ldg(a.bg + 0), Cr);
+    a.out_color[hw + pid] = __fmaf_rn(T, __ldg(a.bg + 1), Cg);
+    a.out_color[2 * hw + pid] = __fmaf_rn(T, __ldg(a.bg + 2), Cb);
+  }
+}
+
+// Reduce 9 per-lane values over the warp.  v[0..7] go through a transposing butterfly (lane L ends
+// up with the warp total of v[(L >> 2) & 7]); v8 through a plain butterfly.
+__device__ __forceinline__ void warp_reduce9(float (&v)[8], float& v8, int lane) {
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+  float r4[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const float keep = h16 ? v[i + 4] : v[i];
+    const float send = h16 ? v[i] : v[i + 4];
+    r4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  float r2[2];
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    const float keep = h8 ? r4[i + 2] : r4[i];
+    const float send = h8 ? r4[i] : r4[i + 2];
+    r2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  {
+    const float keep = h4 ? r2[1] : r2[0];
+    const float send = h4 ? r2[0] : r2[1];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v8 += __shfl_xor_sync(0xffffffffu, v8, o);
+}
+
+// ==================================================================================================
+// K7: compositing adjoint.  Front-to-back replay (same traversal, same ring as the forward): with
+// running transmittance T_j and running prefix colour, the colour composited behind splat j is
+// S_j = C_final - prefix_j, so
+//   dL/dalpha_j = T_j * <c_j, g> - (<S_j, g> + T_final * <bg, g>) / (1 - alpha_j),   g = dL/dpixel
+// which is algebraically the back-to-front recursion of the public algorithm.
+// ==================================================================================================
+__global__ void __launch_bounds__(256) k_render_bwd(RenderBwdArgs a) {
+  __shared__ __align__(128) float4 sm[STAGES][CH * REC_F4];
+  __shared__ __align__(8) uint64_t full[STAGES];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint2 range = a.ranges[blockIdx.y * gridDim.x + blockIdx.x];
+  const uint32_t n = range.y - range.x;
+  const uint32_t nchunks = (n + CH - 1) / CH;
+
+  const int bx = blockIdx.x * TILE + (warp & 1) * 8, by = blockIdx.y * TILE + (warp >> 1) * 4;
+  const int px = bx + (lane & 7), py = by + (lane >> 3);
+  const bool inside = px < a.W && py < a.H;
+  const float pxf = (float)px, pyf = (float)py;
+  const float rx0 = (float)bx, ry0 = (float)by;
+  const float rx1 = (float)min(bx + 7, a.W - 1), ry1 = (float)min(by + 3, a.H - 1);
+
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (nchunks > 0) issue_chunk(a.slab, range.x, n, 0, sm[0], &full[0]);
+    if (nchunks > 1) issue_chunk(a.slab, range.x, n, 1, sm[1], &full[1]);
+  }
+
+  float4 fin = make_float4(0.f, 0.f, 0.f, 1.f);
+  uint32_t ncontrib = 0;
+  float gr = 0.f, gg = 0.f, gb = 0.f;
+  if (inside) {
+    const size_t pid = (size_t)py * a.W + px;
+    const size_t hw = (size_t)a.H * a.W;
+    fin = a.pix[pid];
+    ncontrib = a.n_contrib[pid];
+    gr = __ldg(a.dL_dpix + pid);
+    gg = __ldg(a.dL_dpix + hw + pid);
+    gb = __ldg(a.dL_dpix + 2 * hw + pid);
+  }
+  // T_final * <bg, g>
+  const float bgterm = fin.w * (__ldg(a.bg) * gr + __ldg(a.bg + 1) * gg + __ldg(a.bg + 2) * gb);
+  const float halfW = 0.5f * (float)a.W, halfH = 0.5f * (float)a.H;
+  float T = 1.f, Cr = 0.f, Cg = 0.f, Cb = 0.f;
+
+  for (uint32_t c = 0; c < nchunks; c++) {
+    const int s = c & 1;
+    mbar_wait(&full[s], (c >> 1) & 1);
+    const uint32_t cnt = min((uint32_t)CH, n - c * CH);
+    const float4* st = sm[s];
+    for (uint32_t base = 0; base < cnt; base += 32) {
+      // this pixel is finished once the list position passes its last contributor
+      if (__all_sync(0xffffffffu, c * CH + base >= ncontrib)) break;
+      const uint32_t j = base + lane;
+      bool hit = false;
+      if (j < cnt) {
+        const float4 q0 = st[j * REC_F4], q1 = st[j * REC_F4 + 1];
+        hit = block_may_contribute(q0.x, q0.y, q0.z, q0.w, q1.x, q1.z, rx0, ry0, rx1, ry1);
+      }
+      uint32_t mask = __ballot_sync(0xffffffffu, hit);
+      while (mask) {
+        const int b = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const uint32_t jj = base + b;
+        const float4 q0 = st[jj * REC_F4], q1 = st[jj * REC_F4 + 1], q2 = st[jj * REC_F4 + 2];
+        const float dx = q0.x - pxf, dy = q0.y - pyf;
+        const float power = -0.5f * (q0.z * dx * dx + q1.x * dy * dy) - q0.w * dx * dy;
+        const float G = __expf(power);
+        const float alpha = fminf(0.99f, q1.y * G);
+        const bool valid = (c * CH + jj < ncontrib) && power <= 0.f && alpha >= (1.f / 255.f);
+        if (!__any_sync(0xffffffffu, valid)) continue;
+        float v[8], v8;
+        if (valid) {
+          const float w = alpha * T;
+          Cr = __fmaf_rn(q2.x, w, Cr);
+          Cg = __fmaf_rn(q2.y, w, Cg);
+          Cb = __fmaf_rn(q2.z, w, Cb);
+          const float inv1ma = 1.f / (1.f - alpha);
+          const float behind = (fin.x - Cr) * gr + (fin.y - Cg) * gg + (fin.z - Cb) * gb;
+          const float dL_dalpha = T * (q2.x * gr + q2.y * gg + q2.z * gb) - inv1ma * (behind + bgterm);
+          T = T * (1.f - alpha);
+          const float gv = q1.y * G * dL_dalpha;          // dL/dG * G
+          v[0] = w * gr; v[1] = w * gg; v[2] = w * gb;     // dL/dcolour
+          v[3] = G * dL_dalpha;                            // dL/dopacity
+          v[4] = -gv * (q0.z * dx + q0.w * dy) * halfW;    // dL/dmean2D.x (NDC-scaled)
+          v[5] = -gv * (q1.x * dy + q0.w * dx) * halfH;    // dL/dmean2D.y
+          v[6] = -0.5f * gv * dx * dx;                     // dL/dA
+          v[7] = -gv * dx * dy;                            // dL/dB
+          v8 = -0.5f * gv * dy * dy;                       // dL/dC
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; k++) v[k] = 0.f;
+          v8 = 0.f;
+        }
+        warp_reduce9(v, v8, lane);
+        const uint32_t g = __float_as_uint(q1.w);
+        const bool writer = ((lane & 3) == 0) || lane == 1;
+        if (writer) {
+          const int k = (lane == 1) ? 8 : (lane >> 2);
+          atomicAdd(a.grad2d + (size_t)g * GRAD2D_STRIDE + k, (lane == 1) ? v8 : v[0]);
+        }
+      }
+    }
+    const int num_done = __syncthreads_count(c * CH + cnt >= ncontrib);
+    if (num_done == 256) {
+      if (tid == 0 && c + 1 < nchunks) mbar_wait(&full[(c + 1) & 1], ((c + 1) >> 1) & 1);
+      break;
+    }
+    if (tid == 0 && c + 2 < nchunks) issue_chunk(a.slab, range.x, n, c + 2, sm[s], &full[s]);
+  }
+}
+
+void launch_render(const RenderArgs& a, cudaStream_t st) {
+  const dim3 grid((a.W + TILE - 1) / TILE, (a.H + TILE - 1) / TILE), block(256);
+  k_render_fwd<<<grid, block, 0, st>>>(a);
+  count_launch();
+}
+
+void launch_render_bwd(const RenderBwdArgs& a, cudaStream_t st) {
+  const dim3 grid((a.W + TILE - 1) / TILE, (a.H + TILE - 1) / TILE), block(256);
+  k_render_bwd<<<grid, block, 0, st>>>(a);
+  count_launch();
+}
+
+}  // namespace b200gs

@@ -1,0 +1,214 @@
+"""PyTorch operator surface of the B200 rasterizer -- a drop-in for the Python package of the public
+diff-gaussian-rasterization that BASELINE.json:north_star names (``GaussianRasterizationSettings``,
+``GaussianRasterizer.forward/markVisible``, ``rasterize_gaussians``).  The reference
+repo itself only delegates 3DGS reconstruction/rendering (/root/reference/README.md:75, :29, :85),
+so names, argument meaning and error behaviour mirror that public interface.
+
+Everything below is host-side marshalling; all arithmetic happens in libb200gs.so through the C ABI
+in include/b200gs.h.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import NamedTuple, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _cabi
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+    antialiasing: bool = False
+
+
+RasterizationSettings = GaussianRasterizationSettings
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _opt(t: Optional[torch.Tensor]):
+    """The public interface passes unused optionals as empty tensors; normalise to None."""
+    if t is None or t.numel() == 0:
+        return None
+    return t
+
+
+def _f32c(t: Optional[torch.Tensor], name: str, device) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    if t.device != device:
+        raise ValueError(f"{name} is on {t.device}, expected {device}")
+    return t.contiguous()
+
+
+class _ByteBuffer:
+    """Caller-owned growable scratch buffer handed to the library as a B200GSAlloc."""
+
+    def __init__(self, device):
+        self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
+        self._cb = _cabi.RESIZE_FN(self._resize)
+        self.alloc = _cabi.B200GSAlloc(None, self._cb)
+
+    def _resize(self, _ctx, nbytes):
+        if self.tensor.numel() < nbytes:
+            self.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=self.tensor.device)
+        return self.tensor.data_ptr()
+
+
+def _params(P, M, rs: GaussianRasterizationSettings) -> _cabi.B200GSParams:
+    return _cabi.B200GSParams(int(P), int(rs.sh_degree), int(M), int(rs.image_height), int(rs.image_width),
+                              float(rs.tanfovx), float(rs.tanfovy), float(rs.scale_modifier),
+                              int(bool(rs.prefiltered)), int(bool(rs.debug)))
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                cov3Ds_precomp, raster_settings):
+        L = _cabi.lib()
+        rs = raster_settings
+        if getattr(rs, "antialiasing", False):
+            raise NotImplementedError("antialiasing=True is not implemented by this rasterizer")
+        dev = means3D.device
+        if dev.type != "cuda":
+            raise _cabi.B200GSError("b200gs rasterizer needs CUDA tensors; there is no CPU fallback")
+        means3D = _f32c(means3D, "means3D", dev)
+        sh = _f32c(_opt(sh), "shs", dev)
+        colors_precomp = _f32c(_opt(colors_precomp), "colors_precomp", dev)
+        opacities = _f32c(opacities, "opacities", dev)
+        scales = _f32c(_opt(scales), "scales", dev)
+        rotations = _f32c(_opt(rotations), "rotations", dev)
+        cov3Ds_precomp = _f32c(_opt(cov3Ds_precomp), "cov3D_precomp", dev)
+        bg = _f32c(rs.bg, "bg", dev)
+        view = _f32c(rs.viewmatrix, "viewmatrix", dev)
+        proj = _f32c(rs.projmatrix, "projmatrix", dev)
+        campos = _f32c(rs.campos, "campos", dev)
+
+        P = means3D.shape[0]
+        M = 0 if sh is None else (sh.shape[1] if sh.dim() == 3 else sh.reshape(P, -1, 3).shape[1])
+        H, W = int(rs.image_height), int(rs.image_width)
+        prm = _params(P, M, rs)
+        color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+        radii = torch.empty((P,), dtype=torch.int32, device=dev)
+        geom, binning, img = _ByteBuffer(dev), _ByteBuffer(dev), _ByteBuffer(dev)
+        num_rendered = C.c_int32(0)
+        with torch.cuda.device(dev):
+            stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _cabi.check(L.b200gs_forward(
+                C.byref(prm), _ptr(bg), _ptr(view), _ptr(proj), _ptr(campos), _ptr(means3D), _ptr(sh),
+                _ptr(colors_precomp), _ptr(opacities), _ptr(scales), _ptr(rotations),
+                _ptr(cov3Ds_precomp), _ptr(color), _ptr(radii), geom.alloc, binning.alloc, img.alloc,
+                C.byref(num_rendered), stream))
+        ctx.raster_settings = rs
+        ctx.num_rendered = int(num_rendered.value)
+        ctx.M = M
+        ctx.present = (sh is not None, colors_precomp is not None, scales is not None,
+                       cov3Ds_precomp is not None)
+        z = means3D.new_empty(0)
+        ctx.save_for_backward(means3D, z if sh is None else sh, z if colors_precomp is None else colors_precomp,
+                              opacities, z if scales is None else scales, z if rotations is None else rotations,
+                              z if cov3Ds_precomp is None else cov3Ds_precomp, radii, geom.tensor,
+                              binning.tensor, img.tensor, bg, view, proj, campos)
+        ctx.mark_non_differentiable(radii)
+        return color, radii
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _grad_radii):
+        L = _cabi.lib()
+        rs = ctx.raster_settings
+        (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, radii, geom,
+         binning, img, bg, view, proj, campos) = ctx.saved_tensors
+        has_sh, has_col, has_sr, has_cov = ctx.present
+        sh = sh if has_sh else None
+        colors_precomp = colors_precomp if has_col else None
+        scales = scales if has_sr else None
+        rotations = rotations if has_sr else None
+        cov3Ds_precomp = cov3Ds_precomp if has_cov else None
+        dev = means3D.device
+        P = means3D.shape[0]
+        grad_out_color = grad_out_color.to(torch.float32).contiguous()
+        e = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+        g_means3D, g_means2D, g_opac = e(P, 3), e(P, 3), e(P, 1)
+        g_sh = e(P, ctx.M, 3) if has_sh else None
+        g_col = e(P, 3) if has_col else None
+        g_scales = e(P, 3) if has_sr else None
+        g_rots = e(P, 4) if has_sr else None
+        g_cov = e(P, 6) if has_cov else None
+        prm = _params(P, ctx.M, rs)
+        scratch = _ByteBuffer(dev)
+        with torch.cuda.device(dev):
+            stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _cabi.check(L.b200gs_backward(
+                C.byref(prm), _ptr(bg), _ptr(view), _ptr(proj), _ptr(campos), _ptr(means3D), _ptr(sh),
+                _ptr(colors_precomp), _ptr(opacities), _ptr(scales), _ptr(rotations),
+                _ptr(cov3Ds_precomp), _ptr(radii), _ptr(geom), _ptr(binning), _ptr(img),
+                C.c_int32(ctx.num_rendered), _ptr(grad_out_color), _ptr(g_means3D), _ptr(g_means2D),
+                _ptr(g_sh), _ptr(g_col), _ptr(g_opac), _ptr(g_scales), _ptr(g_rots), _ptr(g_cov),
+                scratch.alloc, stream))
+        # order of the public interface: means3D, means2D, sh, colors_precomp, opacities, scales,
+        # rotations, cov3Ds_precomp, raster_settings
+        return g_means3D, g_means2D, g_sh, g_col, g_opac, g_scales, g_rots, g_cov, None
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                        cov3Ds_precomp, raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                     cov3Ds_precomp, raster_settings)
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings: GaussianRasterizationSettings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions: torch.Tensor) -> torch.Tensor:
+        """Boolean mask of the Gaussians that pass the near-plane cull (view-space z > 0.2)."""
+        L = _cabi.lib()
+        rs = self.raster_settings
+        with torch.no_grad():
+            dev = positions.device
+            if dev.type != "cuda":
+                raise _cabi.B200GSError("b200gs rasterizer needs CUDA tensors; there is no CPU fallback")
+            pos = _f32c(positions, "positions", dev)
+            view = _f32c(rs.viewmatrix, "viewmatrix", dev)
+            proj = _f32c(rs.projmatrix, "projmatrix", dev)
+            out = torch.empty((pos.shape[0],), dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+                _cabi.check(L.b200gs_mark_visible(C.c_int32(pos.shape[0]), _ptr(pos), _ptr(view), _ptr(proj),
+                                                  _ptr(out), stream))
+        return out.bool()
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None,
+                rotations=None, cov3D_precomp=None):
+        rs = self.raster_settings
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception("Please provide excatly one of either SHs or precomputed colors!")
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
+        empty = means3D.new_empty(0)
+        shs = empty if shs is None else shs
+        colors_precomp = empty if colors_precomp is None else colors_precomp
+        scales = empty if scales is None else scales
+        rotations = empty if rotations is None else rotations
+        cov3D_precomp = empty if cov3D_precomp is None else cov3D_precomp
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
+                                   cov3D_precomp, rs)

@@ -1,0 +1,73 @@
+"""The C-ABI library loads and exports every symbol include/b200gs.h declares (no compute calls
+without a GPU), and the host-side operator mirror reproduces the public interface's argument errors."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "b200gs.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200gs_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    from robosimgs_b200 import _cabi
+    L = ctypes.CDLL(_cabi.LIB_PATH)
+    syms = _declared_symbols()
+    assert len(syms) >= 7
+    for s in syms:
+        assert hasattr(L, s), s
+    assert set(syms) == set(_cabi.EXPORTED_SYMBOLS)
+    assert L.b200gs_version() == 100
+
+
+def test_buffer_sizes_are_host_only_and_monotone(built):
+    from robosimgs_b200 import _cabi
+    L = _cabi.lib()
+    g, b, i = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
+    assert L.b200gs_buffer_sizes(1000, 1080, 1920, 50000, ctypes.byref(g), ctypes.byref(b), ctypes.byref(i)) == 0
+    assert g.value >= 1000 * (48 + 6 * 4 + 1) and b.value >= 50000 * 64 and i.value >= 1080 * 1920 * 20
+    g2 = ctypes.c_size_t()
+    L.b200gs_buffer_sizes(2000, 1080, 1920, 0, ctypes.byref(g2), None, None)
+    assert g2.value > g.value
+    assert L.b200gs_buffer_sizes(-1, 10, 10, 0, None, None, None) != 0
+    assert b"invalid" in L.b200gs_last_error()
+
+
+def test_operator_surface_names_and_argument_errors(built):
+    import diff_gaussian_rasterization as dgr
+    import robosimgs_b200 as rb
+    assert dgr.GaussianRasterizer is rb.GaussianRasterizer
+    assert rb.RasterizationSettings is rb.GaussianRasterizationSettings
+    fields = rb.GaussianRasterizationSettings._fields
+    assert fields[:12] == ("image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier",
+                           "viewmatrix", "projmatrix", "sh_degree", "campos", "prefiltered", "debug")
+    from helpers import small_scene
+    sc, cam, rs = small_scene(P=8, degree=0)
+    r = rb.GaussianRasterizer(rs)
+    m2 = torch.zeros_like(sc.means3D)
+    with pytest.raises(Exception, match="SHs or precomputed colors"):
+        r(sc.means3D, m2, sc.opacities, scales=sc.scales, rotations=sc.rotations)
+    with pytest.raises(Exception, match="SHs or precomputed colors"):
+        r(sc.means3D, m2, sc.opacities, shs=sc.shs, colors_precomp=sc.shs[:, 0], scales=sc.scales,
+          rotations=sc.rotations)
+    with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
+        r(sc.means3D, m2, sc.opacities, shs=sc.shs)
+    # no CPU fallback: CPU tensors are refused loudly
+    with pytest.raises(rb.B200GSError, match="no CPU fallback"):
+        r(sc.means3D, m2, sc.opacities, shs=sc.shs, scales=sc.scales, rotations=sc.rotations)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "robosimgs_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "gs_oracle.h" not in txt, f
