@@ -57,6 +57,12 @@ typedef struct B200GSParams {
   float scale_modifier;
   int32_t prefiltered;    /* accepted for signature parity; culled Gaussians are simply skipped */
   int32_t debug;          /* !=0: synchronise and check for errors after every kernel */
+  int64_t pair_capacity_hint; /* 0: size the binning buffer exactly (host waits for D before
+                                 launching the binning stage, as the replaced interface does).
+                                 >0: launch the whole frame for this many (Gaussian,tile) pair
+                                 slots without waiting; D is read back asynchronously and the
+                                 binning stage is redone exactly only if D exceeded the hint.
+                                 Results are identical either way. */
 } B200GSParams;
 
 /* Caller-owned growable byte buffer: resize(ctx, nbytes) returns a device pointer to at least
@@ -76,8 +82,9 @@ typedef struct B200GSAlloc {
  *   geom/binning/img: scratch allocators; *num_rendered receives the number of (Gaussian, tile)
  *   pairs D that were sorted and composited.
  *
- * One device->host read (of D, to size the binning buffer) synchronises the stream, as in the
- * interface this replaces.
+ * With pair_capacity_hint == 0 one device->host read (of D, to size the binning buffer)
+ * synchronises the stream, as in the interface this replaces; with a hint the host only waits on
+ * an event recorded before the binning stage, after the rest of the frame has been queued.
  */
 int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewmatrix,
                    const float* projmatrix, const float* campos, const float* means3D,
@@ -125,6 +132,17 @@ int b200gs_version(void);
 
 /* Kernel launches issued by this process since the last call with reset != 0 (bench accounting). */
 int64_t b200gs_launch_count(int reset);
+
+/*
+ * Optional per-stage device timing (used by bench.py for the roofline figures).  While enabled,
+ * forward/backward bracket each stage with CUDA events on the caller's stream; profile_read()
+ * waits for the recorded events and returns, per stage, the summed milliseconds and the number of
+ * timed launches since the last reset.  Stage i is named b200gs_stage_name(i).
+ */
+#define B200GS_NUM_STAGES 8
+int b200gs_profile_enable(int on);
+int b200gs_profile_read(float* stage_ms, int32_t* stage_calls, int reset);
+const char* b200gs_stage_name(int i);
 
 #ifdef __cplusplus
 }

@@ -14,7 +14,9 @@ LIB_PATH = os.path.join(_HERE, "lib", "libb200gs.so")
 EXPORTED_SYMBOLS = (
     "b200gs_forward", "b200gs_backward", "b200gs_mark_visible", "b200gs_buffer_sizes",
     "b200gs_last_error", "b200gs_version", "b200gs_launch_count",
+    "b200gs_profile_enable", "b200gs_profile_read", "b200gs_stage_name",
 )
+NUM_STAGES = 8
 
 
 class B200GSParams(C.Structure):
@@ -22,7 +24,7 @@ class B200GSParams(C.Structure):
         ("P", C.c_int32), ("sh_degree", C.c_int32), ("M", C.c_int32),
         ("image_height", C.c_int32), ("image_width", C.c_int32),
         ("tanfovx", C.c_float), ("tanfovy", C.c_float), ("scale_modifier", C.c_float),
-        ("prefiltered", C.c_int32), ("debug", C.c_int32),
+        ("prefiltered", C.c_int32), ("debug", C.c_int32), ("pair_capacity_hint", C.c_int64),
     ]
 
 
@@ -69,6 +71,10 @@ def lib():
     L.b200gs_version.restype = C.c_int
     L.b200gs_launch_count.restype = C.c_int64
     L.b200gs_launch_count.argtypes = [C.c_int]
+    L.b200gs_profile_enable.argtypes = [C.c_int]
+    L.b200gs_profile_read.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int]
+    L.b200gs_stage_name.restype = C.c_char_p
+    L.b200gs_stage_name.argtypes = [C.c_int]
     _lib = L
     return L
 
@@ -80,3 +86,16 @@ def check(rc: int) -> None:
 
 def launch_count(reset: bool = False) -> int:
     return int(lib().b200gs_launch_count(1 if reset else 0))
+
+
+def profile_enable(on: bool) -> None:
+    lib().b200gs_profile_enable(1 if on else 0)
+
+
+def profile_read(reset: bool = True) -> dict:
+    """{stage name: (total ms, launches)} accumulated since the last reset."""
+    L = lib()
+    ms = (C.c_float * NUM_STAGES)()
+    calls = (C.c_int32 * NUM_STAGES)()
+    check(L.b200gs_profile_read(ms, calls, 1 if reset else 0))
+    return {L.b200gs_stage_name(i).decode(): (float(ms[i]), int(calls[i])) for i in range(NUM_STAGES)}

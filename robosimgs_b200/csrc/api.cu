@@ -4,6 +4,8 @@
 #include <cstdio>
 #include <cstring>
 #include <atomic>
+#include <mutex>
+#include <vector>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -31,6 +33,37 @@ int debug_sync(const B200GSParams* prm, cudaStream_t s, const char* what) {
   return check_cuda(e, what);
 }
 
+// ---- optional per-stage device timing (bench / roofline accounting) ----------------------------
+static const char* kStageNames[B200GS_NUM_STAGES] = {"project", "depth_sort_scan", "emit_pairs", "tile_sort",
+                                                     "gather_slab", "render", "render_bwd", "project_bwd"};
+struct StageSpan { int stage; cudaEvent_t a, b; };
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<StageSpan> g_spans;
+static std::vector<cudaEvent_t> g_free_events;
+
+static cudaEvent_t prof_event() {
+  cudaEvent_t e;
+  if (!g_free_events.empty()) { e = g_free_events.back(); g_free_events.pop_back(); return e; }
+  cudaEventCreate(&e);
+  return e;
+}
+struct StageTimer {
+  bool on; int stage; cudaStream_t st; cudaEvent_t a;
+  StageTimer(int stage_, cudaStream_t st_) : stage(stage_), st(st_) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    on = g_prof_on;
+    if (on) { a = prof_event(); cudaEventRecord(a, st); }
+  }
+  ~StageTimer() {
+    if (!on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEvent_t b = prof_event();
+    cudaEventRecord(b, st);
+    g_spans.push_back({stage, a, b});
+  }
+};
+
 static int tile_bits_for(int num_tiles) {
   int bits = 1;
   while ((1 << bits) <= num_tiles) bits++;  // room for the invalid id == num_tiles
@@ -48,6 +81,7 @@ static GeomBuf carve_geom(char* base, int P, size_t* bytes) {
   g.tiles = c.take<uint32_t>(P);
   g.offsets = c.take<uint32_t>(P);
   g.clamped = c.take<uint8_t>(P);
+  g.counters = c.take<uint32_t>(32);
   g.cub_temp_bytes = depth_sort_temp_bytes(P);
   g.cub_temp = c.take<char>(g.cub_temp_bytes);
   if (bytes) *bytes = c.bytes();
@@ -122,6 +156,16 @@ static int check_inputs(const B200GSParams* p, const float* means3D, const float
   return 0;
 }
 
+// one pinned word per host thread for the asynchronous read-back of D
+static uint32_t* pinned_slot() {
+  static thread_local uint32_t* slot = nullptr;
+  if (!slot && cudaHostAlloc(reinterpret_cast<void**>(&slot), 64, cudaHostAllocPortable) != cudaSuccess) {
+    set_error("cudaHostAlloc failed for the num_rendered slot");
+    slot = nullptr;
+  }
+  return slot;
+}
+
 static char* grow(B200GSAlloc a, size_t bytes, const char* what) {
   if (!a.resize) { set_error("%s allocator is NULL", what); return nullptr; }
   char* p = a.resize(a.ctx, bytes);
@@ -140,6 +184,29 @@ const char* b200gs_last_error(void) { return g_err; }
 int b200gs_version(void) { return B200GS_VERSION; }
 int64_t b200gs_launch_count(int reset) {
   return reset ? g_launches.exchange(0) : g_launches.load();
+}
+
+int b200gs_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = on != 0;
+  return 0;
+}
+const char* b200gs_stage_name(int i) { return (i >= 0 && i < B200GS_NUM_STAGES) ? kStageNames[i] : ""; }
+int b200gs_profile_read(float* stage_ms, int32_t* stage_calls, int reset) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int i = 0; i < B200GS_NUM_STAGES; i++) { if (stage_ms) stage_ms[i] = 0.f; if (stage_calls) stage_calls[i] = 0; }
+  for (auto& sp : g_spans) {
+    if (cudaEventSynchronize(sp.b) != cudaSuccess) { set_error("profile_read: event sync failed"); return B200GS_ERR_CUDA; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, sp.a, sp.b);
+    if (stage_ms) stage_ms[sp.stage] += ms;
+    if (stage_calls) stage_calls[sp.stage] += 1;
+  }
+  if (reset) {
+    for (auto& sp : g_spans) { g_free_events.push_back(sp.a); g_free_events.push_back(sp.b); }
+    g_spans.clear();
+  }
+  return 0;
 }
 
 int b200gs_buffer_sizes(int32_t P, int32_t H, int32_t W, int64_t D, size_t* geom_bytes,
@@ -190,13 +257,85 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
   pa.view = viewmatrix; pa.proj = projmatrix; pa.campos = campos;
   pa.radii = radii; pa.rec = gb.rec; pa.depth_key = gb.depth_key; pa.idx = gb.idx; pa.tiles = gb.tiles;
   pa.clamped = gb.clamped;
-  launch_project(pa, shs ? prm->sh_degree : -1, st);
+  {
+    StageTimer t(0, st);
+    launch_project(pa, shs ? prm->sh_degree : -1, st);
+  }
   if ((rc = debug_sync(prm, st, "project"))) return rc;
-
-  if ((rc = sort_by_depth_and_scan(gb, P, st))) return rc;
+  {
+    StageTimer t(1, st);
+    if ((rc = sort_by_depth_and_scan(gb, P, st))) return rc;
+  }
   if ((rc = debug_sync(prm, st, "depth sort + scan"))) return rc;
 
+  // ---- binning + compositing for a given pair capacity (D <= cap slots; [D,cap) are padding) ----
+  auto run_binning_and_render = [&](uint32_t cap) -> int {
+    size_t bin_bytes;
+    carve_binning(nullptr, cap, tile_bits, &bin_bytes);
+    char* bin_p = grow(binning, bin_bytes, "binning");
+    if (!bin_p && bin_bytes) return B200GS_ERR_ALLOC;
+    BinBuf bb = carve_binning(bin_p, cap, tile_bits, nullptr);
+    int rc2;
+    if ((rc2 = check_cuda(cudaMemsetAsync(ib.ranges, 0, sizeof(uint2) * (size_t)num_tiles, st), "clear ranges")))
+      return rc2;
+    if (cap > 0) {
+      if ((rc2 = check_cuda(cudaMemsetAsync(gb.counters, 0, 32 * sizeof(uint32_t), st), "clear counters"))) return rc2;
+      EmitArgs ea;
+      ea.P = P; ea.gx = gx; ea.gy = gy; ea.invalid_tile = (uint32_t)num_tiles; ea.capacity = cap;
+      ea.perm = gb.perm; ea.tiles = gb.tiles; ea.offsets = gb.offsets; ea.rec = gb.rec; ea.radii = radii;
+      ea.keys = bb.keys; ea.vals = bb.vals;
+      ea.big_queue = gb.key_sorted; ea.big_count = gb.counters;
+      {
+        StageTimer t(2, st);
+        launch_emit_pairs(ea, st);
+      }
+      if ((rc2 = debug_sync(prm, st, "emit pairs"))) return rc2;
+      {
+        StageTimer t(3, st);
+        if ((rc2 = sort_by_tile(bb, cap, tile_bits, st))) return rc2;
+      }
+      if ((rc2 = debug_sync(prm, st, "tile sort"))) return rc2;
+      GatherArgs ga;
+      ga.D = cap; ga.num_tiles = (uint32_t)num_tiles; ga.keys_sorted = bb.keys_sorted; ga.vals_sorted = bb.vals_sorted;
+      ga.rec = gb.rec; ga.slab = bb.slab; ga.ranges = ib.ranges;
+      {
+        StageTimer t(4, st);
+        launch_gather_slab(ga, st);
+      }
+      if ((rc2 = debug_sync(prm, st, "gather slab"))) return rc2;
+    }
+    RenderArgs ra;
+    ra.W = W; ra.H = H; ra.ranges = ib.ranges; ra.slab = bb.slab; ra.bg = bg; ra.out_color = out_color;
+    ra.pix = ib.pix; ra.n_contrib = ib.n_contrib;
+    {
+      StageTimer t(5, st);
+      launch_render(ra, st);
+    }
+    return debug_sync(prm, st, "render");
+  };
+
   uint32_t D = 0;
+  const int64_t hint = prm->pair_capacity_hint;
+  if (P > 0 && hint > 0 && hint < (int64_t)0x7fffffff) {
+    // Speculative path: D stays on the device.  Its copy to pinned host memory is queued, the rest
+    // of the frame is launched for `hint` pair slots, and only then does the host wait for the copy
+    // (an event early in the stream) -- the GPU never idles while the host learns D.
+    uint32_t* host_d = pinned_slot();
+    if (!host_d) return B200GS_ERR_ALLOC;
+    cudaEvent_t ev;
+    if ((rc = check_cuda(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event create"))) return rc;
+    rc = check_cuda(cudaMemcpyAsync(host_d, gb.offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st),
+                    "queue num_rendered copy");
+    if (!rc) rc = check_cuda(cudaEventRecord(ev, st), "event record");
+    if (!rc) rc = run_binning_and_render((uint32_t)hint);
+    if (!rc) rc = check_cuda(cudaEventSynchronize(ev), "wait num_rendered");
+    cudaEventDestroy(ev);
+    if (rc) return rc;
+    D = *host_d;
+    *num_rendered = (int32_t)D;
+    if ((int64_t)D > hint) return run_binning_and_render(D);   // hint too small: redo exactly
+    return 0;
+  }
   if (P > 0) {
     if ((rc = check_cuda(cudaMemcpyAsync(&D, gb.offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st),
                          "read num_rendered")))
@@ -204,35 +343,7 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
     if ((rc = check_cuda(cudaStreamSynchronize(st), "sync num_rendered"))) return rc;
   }
   *num_rendered = (int32_t)D;
-
-  size_t bin_bytes;
-  carve_binning(nullptr, D, tile_bits, &bin_bytes);
-  char* bin_p = grow(binning, bin_bytes, "binning");
-  if (!bin_p && bin_bytes) return B200GS_ERR_ALLOC;
-  BinBuf bb = carve_binning(bin_p, D, tile_bits, nullptr);
-
-  if ((rc = check_cuda(cudaMemsetAsync(ib.ranges, 0, sizeof(uint2) * (size_t)num_tiles, st), "clear ranges"))) return rc;
-  if (D > 0) {
-    EmitArgs ea;
-    ea.P = P; ea.gx = gx; ea.gy = gy; ea.invalid_tile = (uint32_t)num_tiles;
-    ea.perm = gb.perm; ea.tiles = gb.tiles; ea.offsets = gb.offsets; ea.rec = gb.rec; ea.radii = radii;
-    ea.keys = bb.keys; ea.vals = bb.vals;
-    launch_emit_pairs(ea, st);
-    if ((rc = debug_sync(prm, st, "emit pairs"))) return rc;
-    if ((rc = sort_by_tile(bb, D, tile_bits, st))) return rc;
-    if ((rc = debug_sync(prm, st, "tile sort"))) return rc;
-    GatherArgs ga;
-    ga.D = D; ga.num_tiles = (uint32_t)num_tiles; ga.keys_sorted = bb.keys_sorted; ga.vals_sorted = bb.vals_sorted;
-    ga.rec = gb.rec; ga.slab = bb.slab; ga.ranges = ib.ranges;
-    launch_gather_slab(ga, st);
-    if ((rc = debug_sync(prm, st, "gather slab"))) return rc;
-  }
-
-  RenderArgs ra;
-  ra.W = W; ra.H = H; ra.ranges = ib.ranges; ra.slab = bb.slab; ra.bg = bg; ra.out_color = out_color;
-  ra.pix = ib.pix; ra.n_contrib = ib.n_contrib;
-  launch_render(ra, st);
-  return debug_sync(prm, st, "render");
+  return run_binning_and_render(D);
 }
 
 int b200gs_backward(const B200GSParams* prm, const float* bg, const float* viewmatrix,
@@ -281,7 +392,10 @@ int b200gs_backward(const B200GSParams* prm, const float* bg, const float* viewm
     RenderBwdArgs ra;
     ra.W = W; ra.H = H; ra.ranges = ib.ranges; ra.slab = bb.slab; ra.bg = bg; ra.pix = ib.pix;
     ra.n_contrib = ib.n_contrib; ra.dL_dpix = dL_dout_color; ra.grad2d = grad2d;
-    launch_render_bwd(ra, st);
+    {
+      StageTimer t(6, st);
+      launch_render_bwd(ra, st);
+    }
     if ((rc = debug_sync(prm, st, "render backward"))) return rc;
   }
 
@@ -295,7 +409,10 @@ int b200gs_backward(const B200GSParams* prm, const float* bg, const float* viewm
   pa.radii = radii; pa.tiles = gb.tiles; pa.clamped = gb.clamped; pa.grad2d = grad2d;
   pa.dL_dmeans = dL_dmeans3D; pa.dL_dmeans2D = dL_dmeans2D; pa.dL_dshs = dL_dshs; pa.dL_dcolors = dL_dcolors_precomp;
   pa.dL_dopac = dL_dopacities; pa.dL_dscales = dL_dscales; pa.dL_drots = dL_drotations; pa.dL_dcov3D = dL_dcov3D;
-  launch_project_bwd(pa, shs ? prm->sh_degree : -1, st);
+  {
+    StageTimer t(7, st);
+    launch_project_bwd(pa, shs ? prm->sh_degree : -1, st);
+  }
   return debug_sync(prm, st, "project backward");
 }
 

@@ -44,6 +44,7 @@ struct GeomBuf {
   uint32_t* tiles;      // [P] tiles touched (tight count)
   uint32_t* offsets;    // [P] inclusive scan of tiles[perm[i]]
   uint8_t* clamped;     // [P] bit c set: colour channel c was clamped at 0
+  uint32_t* counters;   // [32] device-side scalars (large-footprint queue length, ...)
   char* cub_temp;
   size_t cub_temp_bytes;
 };

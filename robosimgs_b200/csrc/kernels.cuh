@@ -18,10 +18,13 @@ struct ProjectArgs {
 struct EmitArgs {
   int P, gx, gy;
   uint32_t invalid_tile;
+  uint32_t capacity;   // number of pair slots in keys/vals; slots [D, capacity) are padded
   const uint32_t *perm, *tiles, *offsets;
   const float4* rec;
   const int32_t* radii;
   uint32_t *keys, *vals;
+  uint32_t* big_queue;  // [P] ranks of large-footprint Gaussians (reuses the sorted-key buffer)
+  uint32_t* big_count;  // [1] zeroed before the emission stage
 };
 
 struct GatherArgs {

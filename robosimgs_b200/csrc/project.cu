@@ -153,6 +153,8 @@ __device__ __forceinline__ void load_sh_row(const float* __restrict__ row, bool 
 // that the ellipse {0.5 q <= thr} cannot reach contribute nothing to the image or to any gradient,
 // so they are dropped: coverage = reference rect  intersected with  per-tile-row ellipse spans.
 // thr carries a +0.01 slack (alpha ratio 1%) so fp32 rounding can only add pairs, never lose one.
+constexpr uint32_t EMIT_BIG_THRESHOLD = 96;  // tiles; above this a whole warp emits the Gaussian
+
 struct TileRect {
   int x0, y0, x1, y1;  // [x0,x1) x [y0,y1) in tiles
 };
@@ -343,30 +345,112 @@ __global__ void __launch_bounds__(256) k_project(ProjectArgs a) {
 // ==================================================================================================
 __global__ void __launch_bounds__(256) k_emit_pairs(EmitArgs a) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= a.P) return;
-  const uint32_t g = a.perm[r];
-  const uint32_t n = a.tiles[g];
-  if (n == 0) return;
-  uint32_t off = a.offsets[r] - n;
-  const uint32_t end = off + n;
-  const float4 q0 = a.rec[(size_t)g * REC_F4], q1 = a.rec[(size_t)g * REC_F4 + 1];
-  const TileRect rect = reference_rect(q0.x, q0.y, a.radii[g], a.gx, a.gy);
-  SpanCtx s;
-  if (span_setup(s, q0.x, q0.y, q0.z, q0.w, q1.x, q1.z)) {
-    for (int ty = rect.y0; ty < rect.y1; ty++) {
-      int c0, c1;
-      row_span(s, rect, ty, c0, c1);
-      for (int tx = c0; tx < c1 && off < end; tx++) {
-        a.keys[off] = (uint32_t)(ty * a.gx + tx);
-        a.vals[off] = g;
-        off++;
-      }
+  const int lane = threadIdx.x & 31;
+  const uint32_t cap = a.capacity;
+  const bool valid = r < a.P;
+  uint32_t g = 0, n = 0, off = 0;
+  float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
+  int radius = 0;
+  if (valid) {
+    g = a.perm[r];
+    n = a.tiles[g];
+    if (n) {
+      off = a.offsets[r] - n;
+      q0 = a.rec[(size_t)g * REC_F4];
+      q1 = a.rec[(size_t)g * REC_F4 + 1];
+      radius = a.radii[g];
     }
   }
-  // defensive: never leave unwritten slots (cannot happen; count and emit share band_x_extent)
-  for (; off < end; off++) {
-    a.keys[off] = a.invalid_tile;
-    a.vals[off] = g;
+  // ---- small footprints: one thread writes its own pairs ----
+  const bool big = n > EMIT_BIG_THRESHOLD;
+  if (n > 0 && !big) {
+    const uint32_t end = off + n;
+    uint32_t o = off;
+    const TileRect rect = reference_rect(q0.x, q0.y, radius, a.gx, a.gy);
+    SpanCtx s;
+    if (span_setup(s, q0.x, q0.y, q0.z, q0.w, q1.x, q1.z)) {
+      for (int ty = rect.y0; ty < rect.y1; ty++) {
+        int c0, c1;
+        row_span(s, rect, ty, c0, c1);
+        for (int tx = c0; tx < c1 && o < end; tx++, o++) {
+          if (o < cap) {
+            a.keys[o] = (uint32_t)(ty * a.gx + tx);
+            a.vals[o] = g;
+          }
+        }
+      }
+    }
+    // defensive: never leave unwritten slots (count and emit share band_x_extent, so o == end)
+    for (; o < end; o++) {
+      if (o < cap) { a.keys[o] = a.invalid_tile; a.vals[o] = g; }
+    }
+  }
+  // ---- large footprints go to a global queue; k_emit_big spreads them over the whole GPU (they
+  // are depth-sorted, i.e. the nearest = largest splats would otherwise pile up in a few warps) ----
+  if (big) a.big_queue[atomicAdd(a.big_count, 1u)] = (uint32_t)r;
+  // ---- speculative capacity: pad [D, capacity) with the invalid tile id so the sort can run on a
+  // host-known item count while D is still on the device ----
+  if (cap > 0) {
+    const uint32_t D = a.P > 0 ? a.offsets[a.P - 1] : 0u;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = D + (uint32_t)r; i < cap; i += stride) {
+      a.keys[i] = a.invalid_tile;
+      a.vals[i] = 0u;
+    }
+  }
+}
+
+// One warp per queued large-footprint Gaussian: lanes compute the spans of 32 tile rows in parallel,
+// a warp scan turns the span lengths into output offsets, then each row's tiles are written with
+// coalesced 32-wide stores.
+__global__ void __launch_bounds__(256) k_emit_big(EmitArgs a) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t count = *a.big_count;
+  const uint32_t cap = a.capacity;
+  for (uint32_t w = warp_global; w < count; w += nwarps) {
+    const uint32_t r = a.big_queue[w];
+    const uint32_t g = a.perm[r];
+    const uint32_t n = a.tiles[g];
+    const uint32_t off = a.offsets[r] - n, end = off + n;
+    const float4 q0 = a.rec[(size_t)g * REC_F4], q1 = a.rec[(size_t)g * REC_F4 + 1];
+    const TileRect rect = reference_rect(q0.x, q0.y, a.radii[g], a.gx, a.gy);
+    SpanCtx s;
+    const bool ok = span_setup(s, q0.x, q0.y, q0.z, q0.w, q1.x, q1.z);
+    uint32_t o = off;
+    for (int y_base = rect.y0; ok && y_base < rect.y1; y_base += 32) {
+      const int ty = y_base + lane;
+      int c0 = 0, c1 = 0;
+      if (ty < rect.y1) row_span(s, rect, ty, c0, c1);
+      const uint32_t len = (uint32_t)(c1 - c0);
+      uint32_t incl = len;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+      }
+      const uint32_t row_off = o + incl - len;
+      const int rows = min(32, rect.y1 - y_base);
+      for (int i = 0; i < rows; i++) {
+        const uint32_t l_i = __shfl_sync(0xffffffffu, len, i);
+        if (l_i == 0) continue;
+        const uint32_t o_i = __shfl_sync(0xffffffffu, row_off, i);
+        const int c_i = __shfl_sync(0xffffffffu, c0, i);
+        const uint32_t tile0 = (uint32_t)((y_base + i) * a.gx + c_i);
+        for (uint32_t k = lane; k < l_i; k += 32) {
+          const uint32_t idx = o_i + k;
+          if (idx < end && idx < cap) {
+            a.keys[idx] = tile0 + k;
+            a.vals[idx] = g;
+          }
+        }
+      }
+      o += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    for (uint32_t idx = min(o, end) + lane; idx < end; idx += 32) {
+      if (idx < cap) { a.keys[idx] = a.invalid_tile; a.vals[idx] = g; }
+    }
   }
 }
 
@@ -377,15 +461,14 @@ __global__ void __launch_bounds__(256) k_gather_slab(GatherArgs a) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= a.D) return;
   const uint32_t t = a.keys_sorted[j];
+  if (t >= a.num_tiles) return;   // padding of the speculative capacity
   const uint32_t g = a.vals_sorted[j];
   const float4* src = a.rec + (size_t)g * REC_F4;
   const float4 q0 = __ldg(src), q1 = __ldg(src + 1), q2 = __ldg(src + 2);
   float4* dst = a.slab + (size_t)j * REC_F4;
   dst[0] = q0; dst[1] = q1; dst[2] = q2;
-  if (t < a.num_tiles) {
-    if (j == 0 || a.keys_sorted[j - 1] != t) a.ranges[t].x = (uint32_t)j;
-    if (j == a.D - 1 || a.keys_sorted[j + 1] != t) a.ranges[t].y = (uint32_t)(j + 1);
-  }
+  if (j == 0 || a.keys_sorted[j - 1] != t) a.ranges[t].x = (uint32_t)j;
+  if (j == a.D - 1 || a.keys_sorted[j + 1] != t) a.ranges[t].y = (uint32_t)(j + 1);
 }
 
 // ==================================================================================================
@@ -660,7 +743,8 @@ void launch_project(const ProjectArgs& a, int deg, cudaStream_t st) {
 void launch_emit_pairs(const EmitArgs& a, cudaStream_t st) {
   if (a.P == 0) return;
   k_emit_pairs<<<(a.P + 255) / 256, 256, 0, st>>>(a);
-  count_launch();
+  k_emit_big<<<148 * 4, 256, 0, st>>>(a);
+  count_launch(2);
 }
 
 void launch_gather_slab(const GatherArgs& a, cudaStream_t st) {

@@ -68,14 +68,25 @@ class _ByteBuffer:
 
     def _resize(self, _ctx, nbytes):
         if self.tensor.numel() < nbytes:
-            self.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=self.tensor.device)
+            # round up to 4 significant bits so frame-to-frame size changes hit the same cached
+            # block of torch's allocator instead of a fresh cudaMalloc
+            n = int(nbytes)
+            g = 1 << max(n.bit_length() - 4, 9)
+            self.tensor = torch.empty((n + g - 1) // g * g, dtype=torch.uint8, device=self.tensor.device)
         return self.tensor.data_ptr()
 
 
-def _params(P, M, rs: GaussianRasterizationSettings) -> _cabi.B200GSParams:
+# Pair-capacity hints (see B200GSParams.pair_capacity_hint): the number of (Gaussian,tile) pairs of
+# the previous frame with the same (device, P, H, W), plus head-room.  Purely a performance hint --
+# the library redoes the binning stage exactly if a frame needs more.
+_PAIR_HINTS: dict = {}
+SPECULATE_PAIR_CAPACITY = True
+
+
+def _params(P, M, rs: GaussianRasterizationSettings, hint: int = 0) -> _cabi.B200GSParams:
     return _cabi.B200GSParams(int(P), int(rs.sh_degree), int(M), int(rs.image_height), int(rs.image_width),
                               float(rs.tanfovx), float(rs.tanfovy), float(rs.scale_modifier),
-                              int(bool(rs.prefiltered)), int(bool(rs.debug)))
+                              int(bool(rs.prefiltered)), int(bool(rs.debug)), int(hint))
 
 
 class _RasterizeGaussians(torch.autograd.Function):
@@ -104,7 +115,9 @@ class _RasterizeGaussians(torch.autograd.Function):
         P = means3D.shape[0]
         M = 0 if sh is None else (sh.shape[1] if sh.dim() == 3 else sh.reshape(P, -1, 3).shape[1])
         H, W = int(rs.image_height), int(rs.image_width)
-        prm = _params(P, M, rs)
+        hint_key = (dev.index, P, H, W)
+        last_D = _PAIR_HINTS.get(hint_key, 0) if SPECULATE_PAIR_CAPACITY and not rs.debug else 0
+        prm = _params(P, M, rs, last_D + (last_D >> 4) + 32768 if last_D > 0 else 0)
         color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
         radii = torch.empty((P,), dtype=torch.int32, device=dev)
         geom, binning, img = _ByteBuffer(dev), _ByteBuffer(dev), _ByteBuffer(dev)
@@ -118,6 +131,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                 C.byref(num_rendered), stream))
         ctx.raster_settings = rs
         ctx.num_rendered = int(num_rendered.value)
+        _PAIR_HINTS[hint_key] = ctx.num_rendered
         ctx.M = M
         ctx.present = (sh is not None, colors_precomp is not None, scales is not None,
                        cov3Ds_precomp is not None)
