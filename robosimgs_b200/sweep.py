@@ -1,0 +1,119 @@
+"""Camera-sharded render sweep: one process per GPU, scene replicated once,
+camera f -> rank f mod world, no data-path collective.  This is the datagen pattern of the
+reference's (unreleased) per-frame scene renderer (/root/reference/README.md:29,85).
+
+    torchrun --nproc-per-node N -m robosimgs_b200.sweep --cameras 64 --gaussians 3000000
+"""
+from __future__ import annotations
+
+import os
+from typing import Callable, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from .cameras import Camera
+
+SCENE_FIELDS = ("means3D", "shs", "opacities", "scales", "rotations")
+
+
+def shard_indices(n_items: int, rank: int, world: int) -> List[int]:
+    """Round-robin camera -> rank assignment."""
+    return list(range(rank, n_items, world))
+
+
+def replicate_scene(tensors: Optional[dict], device, src: int = 0) -> dict:
+    """Broadcast the packed scene from `src` to every rank (shapes first, then one collective per
+    tensor).  With world size 1 this is just a device transfer."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    if world == 1:
+        return {k: tensors[k].to(device) for k in SCENE_FIELDS}
+    shapes = [list(tensors[k].shape) for k in SCENE_FIELDS] if rank == src else None
+    box = [shapes]
+    dist.broadcast_object_list(box, src=src)
+    out = {}
+    for k, shp in zip(SCENE_FIELDS, box[0]):
+        t = tensors[k].to(device) if rank == src else torch.empty(shp, dtype=torch.float32, device=device)
+        dist.broadcast(t, src=src)
+        out[k] = t
+    return out
+
+
+def default_render_fn(scene: dict, sh_degree: int, bg: torch.Tensor) -> Callable[[Camera], torch.Tensor]:
+    from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+    dev = scene["means3D"].device
+    means2D = torch.zeros_like(scene["means3D"])
+
+    def render(cam: Camera) -> torch.Tensor:
+        rs = GaussianRasterizationSettings(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy, bg, 1.0,
+                                           cam.viewmatrix.to(dev, non_blocking=True),
+                                           cam.projmatrix.to(dev, non_blocking=True), sh_degree,
+                                           cam.campos.to(dev, non_blocking=True), False, False)
+        with torch.no_grad():
+            color, _ = GaussianRasterizer(rs)(scene["means3D"], means2D, scene["opacities"], shs=scene["shs"],
+                                              scales=scene["scales"], rotations=scene["rotations"])
+        return color
+    return render
+
+
+def render_sweep(cameras: Sequence[Camera], render_fn: Callable[[Camera], torch.Tensor],
+                 on_frame: Optional[Callable[[int, torch.Tensor], None]] = None, gather: bool = False):
+    """Render this rank's share of `cameras`.  `on_frame(global_index, frame)` is called per frame
+    (e.g. to write it to the dataset).  With gather=True rank 0 receives every frame's mean as a
+    cheap completion record (frames themselves stay with the rank that rendered them)."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    mine = shard_indices(len(cameras), rank, world)
+    means = torch.zeros(len(cameras), dtype=torch.float64)
+    for f in mine:
+        frame = render_fn(cameras[f])
+        if on_frame is not None:
+            on_frame(f, frame)
+        means[f] = frame.double().mean().item()
+    if gather and world > 1:
+        dev = means.device if dist.get_backend() == "gloo" else torch.device("cuda", torch.cuda.current_device())
+        m = means.to(dev)
+        dist.all_reduce(m)          # disjoint supports -> sum == gather
+        means = m.cpu()
+    return mine, means
+
+
+def main():
+    import argparse
+    import time
+    from .scenes import sweep_scene
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cameras", type=int, default=64)
+    ap.add_argument("--gaussians", type=int, default=3_000_000)
+    a = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    sc, cams = sweep_scene(a.gaussians, a.cameras)
+    scene = replicate_scene({k: getattr(sc, k) for k in SCENE_FIELDS} if rank == 0 else None, dev)
+    render = default_render_fn(scene, sc.sh_degree, torch.zeros(3, device=dev))
+    render(cams[rank % len(cams)])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    mine, means = render_sweep(cams, render, gather=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dt = time.perf_counter() - t0
+    if rank == 0:
+        print(f"[sweep] {len(cams)} cameras on {world} GPU(s): {len(cams) / dt:.1f} frames/s, "
+              f"mean of frame means {float(means.mean()):.6f}")
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
