@@ -35,7 +35,7 @@ int debug_sync(const B200GSParams* prm, cudaStream_t s, const char* what) {
 
 // ---- optional per-stage device timing (bench / roofline accounting) ----------------------------
 static const char* kStageNames[B200GS_NUM_STAGES] = {"project", "depth_sort_scan", "emit_pairs", "tile_sort",
-                                                     "gather_slab", "render", "render_bwd", "project_bwd"};
+                                                     "tile_ranges", "render", "render_bwd", "project_bwd"};
 struct StageSpan { int stage; cudaEvent_t a, b; };
 static std::mutex g_prof_mu;
 static bool g_prof_on = false;
@@ -91,11 +91,10 @@ static GeomBuf carve_geom(char* base, int P, size_t* bytes) {
 static BinBuf carve_binning(char* base, int64_t D, int tile_bits, size_t* bytes) {
   Carver c(base);
   BinBuf b;
-  b.slab = c.take<float4>((size_t)D * REC_F4);
+  b.vals_sorted = c.take<uint32_t>(D);
+  b.keys_sorted = c.take<uint32_t>(D);
   b.keys = c.take<uint32_t>(D);
   b.vals = c.take<uint32_t>(D);
-  b.keys_sorted = c.take<uint32_t>(D);
-  b.vals_sorted = c.take<uint32_t>(D);
   b.cub_temp_bytes = tile_sort_temp_bytes(D, tile_bits);
   b.cub_temp = c.take<char>(b.cub_temp_bytes);
   if (bytes) *bytes = c.bytes();
@@ -295,17 +294,17 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
         if ((rc2 = sort_by_tile(bb, cap, tile_bits, st))) return rc2;
       }
       if ((rc2 = debug_sync(prm, st, "tile sort"))) return rc2;
-      GatherArgs ga;
-      ga.D = cap; ga.num_tiles = (uint32_t)num_tiles; ga.keys_sorted = bb.keys_sorted; ga.vals_sorted = bb.vals_sorted;
-      ga.rec = gb.rec; ga.slab = bb.slab; ga.ranges = ib.ranges;
+      RangesArgs ga;
+      ga.D = cap; ga.num_tiles = (uint32_t)num_tiles; ga.keys_sorted = bb.keys_sorted; ga.ranges = ib.ranges;
       {
         StageTimer t(4, st);
-        launch_gather_slab(ga, st);
+        launch_tile_ranges(ga, st);
       }
-      if ((rc2 = debug_sync(prm, st, "gather slab"))) return rc2;
+      if ((rc2 = debug_sync(prm, st, "tile ranges"))) return rc2;
     }
     RenderArgs ra;
-    ra.W = W; ra.H = H; ra.ranges = ib.ranges; ra.slab = bb.slab; ra.bg = bg; ra.out_color = out_color;
+    ra.W = W; ra.H = H; ra.ranges = ib.ranges; ra.point_list = bb.vals_sorted; ra.rec = gb.rec; ra.bg = bg;
+    ra.out_color = out_color;
     ra.pix = ib.pix; ra.n_contrib = ib.n_contrib;
     {
       StageTimer t(5, st);
@@ -390,7 +389,8 @@ int b200gs_backward(const B200GSParams* prm, const float* bg, const float* viewm
 
   if (num_rendered > 0) {
     RenderBwdArgs ra;
-    ra.W = W; ra.H = H; ra.ranges = ib.ranges; ra.slab = bb.slab; ra.bg = bg; ra.pix = ib.pix;
+    ra.W = W; ra.H = H; ra.ranges = ib.ranges; ra.point_list = bb.vals_sorted; ra.rec = gb.rec; ra.bg = bg;
+    ra.pix = ib.pix;
     ra.n_contrib = ib.n_contrib; ra.dL_dpix = dL_dout_color; ra.grad2d = grad2d;
     {
       StageTimer t(6, st);

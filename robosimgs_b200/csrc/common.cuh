@@ -16,9 +16,8 @@ constexpr int GRAD2D_STRIDE = 12;   // floats per Gaussian in the screen-space g
 //   q0 = { x, y, A, B }            pixel centre, conic
 //   q1 = { C, opacity, thr, idx }  thr = ln(255*opacity) + slack: 0.5*q <= thr  <=>  alpha >= 1/255
 //   q2 = { r, g, b, depth }
-// The same layout is used per Gaussian (geom buffer) and per (Gaussian,tile) pair in tile-sorted
-// order (binning buffer "slab"), so a tile's slab is one contiguous, 16-byte aligned byte range
-// that a single TMA bulk copy can fetch.
+// One record per Gaussian (geom buffer, 16-byte aligned): the unit a single 48-byte TMA bulk copy
+// gathers into a compositing CTA's shared-memory ring.
 
 // ---- buffer carving (128-byte aligned chunks inside caller-owned byte buffers) -----------------
 struct Carver {
@@ -50,11 +49,11 @@ struct GeomBuf {
 };
 
 struct BinBuf {
-  float4* slab;         // [D*3] records in (tile, depth) order
-  uint32_t* keys;       // [D] tile ids, emit order (depth-major)
-  uint32_t* vals;       // [D] Gaussian ids
-  uint32_t* keys_sorted;
-  uint32_t* vals_sorted;
+  uint32_t* vals_sorted; // [D] Gaussian ids in (tile, depth) order -- FIRST chunk: the only part the
+                         // backward pass reads, so its offset must not depend on the capacity
+  uint32_t* keys_sorted; // [D]
+  uint32_t* keys;        // [D] tile ids, emit order (depth-major)
+  uint32_t* vals;        // [D] Gaussian ids
   char* cub_temp;
   size_t cub_temp_bytes;
 };

@@ -27,19 +27,18 @@ struct EmitArgs {
   uint32_t* big_count;  // [1] zeroed before the emission stage
 };
 
-struct GatherArgs {
-  int64_t D;
+struct RangesArgs {
+  int64_t D;           // sorted pair slots (incl. padding of the speculative capacity)
   uint32_t num_tiles;
-  const uint32_t *keys_sorted, *vals_sorted;
-  const float4* rec;
-  float4* slab;
+  const uint32_t* keys_sorted;
   uint2* ranges;
 };
 
 struct RenderArgs {
   int W, H;
   const uint2* ranges;
-  const float4* slab;
+  const uint32_t* point_list;  // Gaussian ids in (tile, depth) order
+  const float4* rec;           // [P] projected-splat records
   const float* bg;
   float* out_color;     // [3][H][W]
   float4* pix;          // [H*W]
@@ -49,7 +48,8 @@ struct RenderArgs {
 struct RenderBwdArgs {
   int W, H;
   const uint2* ranges;
-  const float4* slab;
+  const uint32_t* point_list;
+  const float4* rec;
   const float* bg;
   const float4* pix;
   const uint32_t* n_contrib;
@@ -71,7 +71,7 @@ struct ProjectBwdArgs {
 
 void launch_project(const ProjectArgs& a, int deg, cudaStream_t st);
 void launch_emit_pairs(const EmitArgs& a, cudaStream_t st);
-void launch_gather_slab(const GatherArgs& a, cudaStream_t st);
+void launch_tile_ranges(const RangesArgs& a, cudaStream_t st);
 void launch_mark_visible(int P, const float* means, const float* view, uint8_t* present, cudaStream_t st);
 void launch_project_bwd(const ProjectBwdArgs& a, int deg, cudaStream_t st);
 void launch_render(const RenderArgs& a, cudaStream_t st);

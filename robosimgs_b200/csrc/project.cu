@@ -455,18 +455,13 @@ __global__ void __launch_bounds__(256) k_emit_big(EmitArgs a) {
 }
 
 // ==================================================================================================
-// K5 + slab gather: per sorted pair, copy the 48-byte record into tile order and mark tile ranges.
+// K5: per-tile [start,end) in the sorted pair list
 // ==================================================================================================
-__global__ void __launch_bounds__(256) k_gather_slab(GatherArgs a) {
+__global__ void __launch_bounds__(256) k_tile_ranges(RangesArgs a) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= a.D) return;
   const uint32_t t = a.keys_sorted[j];
   if (t >= a.num_tiles) return;   // padding of the speculative capacity
-  const uint32_t g = a.vals_sorted[j];
-  const float4* src = a.rec + (size_t)g * REC_F4;
-  const float4 q0 = __ldg(src), q1 = __ldg(src + 1), q2 = __ldg(src + 2);
-  float4* dst = a.slab + (size_t)j * REC_F4;
-  dst[0] = q0; dst[1] = q1; dst[2] = q2;
   if (j == 0 || a.keys_sorted[j - 1] != t) a.ranges[t].x = (uint32_t)j;
   if (j == a.D - 1 || a.keys_sorted[j + 1] != t) a.ranges[t].y = (uint32_t)(j + 1);
 }
@@ -747,9 +742,9 @@ void launch_emit_pairs(const EmitArgs& a, cudaStream_t st) {
   count_launch(2);
 }
 
-void launch_gather_slab(const GatherArgs& a, cudaStream_t st) {
+void launch_tile_ranges(const RangesArgs& a, cudaStream_t st) {
   if (a.D == 0) return;
-  k_gather_slab<<<(unsigned)((a.D + 255) / 256), 256, 0, st>>>(a);
+  k_tile_ranges<<<(unsigned)((a.D + 255) / 256), 256, 0, st>>>(a);
   count_launch();
 }
 

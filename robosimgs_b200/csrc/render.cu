@@ -7,9 +7,12 @@
 //
 // B200 design:
 //  * one CTA per 16x16 tile, 8 warps, each warp owns an 8x4 pixel block;
-//  * the tile's splat records are one contiguous 48-byte-record slab in HBM; chunks of 256 records
-//    are fetched with 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP) into a 2-stage shared-memory
-//    ring signalled through mbarriers -- no thread spends registers or issue slots on the fetch;
+//  * a tile's splats are a contiguous range of the sorted Gaussian-id list; the 48-byte projected
+//    records (L2-resident table, P_vis * 48 B) are gathered straight into a 2-stage shared-memory
+//    ring, 256 records per stage, by asynchronous copies that bypass the register file: one 48-byte
+//    TMA bulk copy per record (cp.async.bulk, SASS UBLKCP) completing on the stage's mbarrier
+//    (GATHER_TMA) or three 16-byte cp.async (LDGSTS) per record (GATHER_LDGSTS).  No tile-ordered
+//    copy of the records ("slab") is ever written to HBM;
 //  * hierarchical culling: 32 lanes test 32 different records against the warp's 8x4 pixel block
 //    (exact minimum of the conic form over the block), one ballot, and only the surviving records
 //    are evaluated per pixel -- records are read from shared memory as 128-bit broadcasts;
@@ -17,6 +20,8 @@
 //  * adjoint: gradients of a record are reduced over the warp with a transposing butterfly
 //    (14 shuffles for 9 values) and leave the SM as one 9-lane RED.ADD.F32 to a 48-byte aligned
 //    accumulator row per Gaussian.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -45,22 +50,93 @@ __device__ __forceinline__ bool block_may_contribute(float x, float y, float A, 
   return 0.5f * q - 4e-6f * mag <= thr;
 }
 
-struct RingState {
-  uint32_t n;        // records in this tile
-  uint32_t nchunks;
-};
+enum { GATHER_TMA = 0, GATHER_LDGSTS = 1 };
 
-__device__ __forceinline__ void issue_chunk(const float4* slab, uint32_t start, uint32_t n, uint32_t c,
-                                            float4* stage, uint64_t* bar) {
-  const uint32_t cnt = min((uint32_t)CH, n - c * CH);
-  const uint32_t bytes = cnt * REC_F4 * 16;
-  mbar_expect_tx(bar, bytes);
-  tma_load_1d(stage, slab + (size_t)(start + c * CH) * REC_F4, bytes, bar);
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Shared-memory ring of gathered splat records, filled cooperatively by the CTA's 256 threads.
+// Thread t owns slot t of every stage; the Gaussian id for the *next* fill is prefetched into a
+// register one chunk ahead so the dependent gather never waits on the id load.
+template <int MODE>
+struct GatherRing {
+  float4 (*sm)[CH * REC_F4];
+  uint64_t* full;
+  const uint32_t* list;   // sorted Gaussian ids of this tile
+  const float4* rec;
+  uint32_t n, nchunks;
+  uint32_t next_id;       // id for slot tid of chunk `next_chunk`
+  int tid;
+
+  __device__ __forceinline__ uint32_t count(uint32_t c) const { return min((uint32_t)CH, n - c * CH); }
+  __device__ __forceinline__ uint32_t load_id(uint32_t c) const {
+    return (c < nchunks && (uint32_t)tid < count(c)) ? __ldg(list + c * CH + tid) : 0u;
+  }
+  // issue the gather of chunk c into stage c&1 using id (all threads call)
+  __device__ __forceinline__ void issue(uint32_t c, uint32_t id) {
+    const int s = c & 1;
+    if (c < nchunks) {
+      const uint32_t cnt = count(c);
+      if (MODE == GATHER_TMA) {
+        if ((uint32_t)tid < cnt) tma_load_1d(&sm[s][tid * REC_F4], rec + (size_t)id * REC_F4, REC_F4 * 16, &full[s]);
+        if (tid == 0) mbar_expect_tx(&full[s], cnt * REC_F4 * 16);
+      } else {
+        if ((uint32_t)tid < cnt) {
+          const float4* src = rec + (size_t)id * REC_F4;
+          cp_async16(&sm[s][tid * REC_F4], src);
+          cp_async16(&sm[s][tid * REC_F4 + 1], src + 1);
+          cp_async16(&sm[s][tid * REC_F4 + 2], src + 2);
+        }
+      }
+    }
+    if (MODE == GATHER_LDGSTS) cp_async_commit();   // one (possibly empty) group per call
+  }
+  __device__ __forceinline__ void prologue() {
+    if (MODE == GATHER_TMA) {
+      if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        mbar_fence_init();
+      }
+      __syncthreads();
+    }
+    const uint32_t id0 = load_id(0), id1 = load_id(1);
+    issue(0, id0);
+    issue(1, id1);
+    next_id = load_id(2);
+  }
+  // block until chunk c is resident in stage c&1 (all threads call)
+  __device__ __forceinline__ void wait(uint32_t c) {
+    if (MODE == GATHER_TMA) {
+      mbar_wait(&full[c & 1], (c >> 1) & 1);
+    } else {
+      cp_async_wait<1>();
+      __syncthreads();
+    }
+  }
+  // stage c&1 is free (caller synchronised the CTA): refill it with chunk c+2
+  __device__ __forceinline__ void refill(uint32_t c) {
+    issue(c + 2, next_id);
+    next_id = load_id(c + 3);
+  }
+  // leave no asynchronous copy in flight into this CTA's shared memory
+  __device__ __forceinline__ void drain(uint32_t c) {
+    if (MODE == GATHER_TMA) {
+      if (tid == 0 && c + 1 < nchunks) mbar_wait(&full[(c + 1) & 1], ((c + 1) >> 1) & 1);
+    } else {
+      cp_async_wait<0>();
+    }
+  }
+};
 
 // ==================================================================================================
 // K6: forward compositing
 // ==================================================================================================
+template <int MODE>
 __global__ void __launch_bounds__(256) k_render_fwd(RenderArgs a) {
   __shared__ __align__(128) float4 sm[STAGES][CH * REC_F4];
   __shared__ __align__(8) uint64_t full[STAGES];
@@ -69,6 +145,7 @@ __global__ void __launch_bounds__(256) k_render_fwd(RenderArgs a) {
   const uint2 range = a.ranges[blockIdx.y * gridDim.x + blockIdx.x];
   const uint32_t n = range.y - range.x;
   const uint32_t nchunks = (n + CH - 1) / CH;
+  GatherRing<MODE> ring{sm, full, a.point_list + range.x, a.rec, n, nchunks, 0u, tid};
 
   const int bx = blockIdx.x * TILE + (warp & 1) * 8, by = blockIdx.y * TILE + (warp >> 1) * 4;
   const int px = bx + (lane & 7), py = by + (lane >> 3);
@@ -77,16 +154,7 @@ __global__ void __launch_bounds__(256) k_render_fwd(RenderArgs a) {
   const float rx0 = (float)bx, ry0 = (float)by;
   const float rx1 = (float)min(bx + 7, a.W - 1), ry1 = (float)min(by + 3, a.H - 1);
 
-  if (tid == 0) {
-    mbar_init(&full[0], 1);
-    mbar_init(&full[1], 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
-  if (tid == 0) {
-    if (nchunks > 0) issue_chunk(a.slab, range.x, n, 0, sm[0], &full[0]);
-    if (nchunks > 1) issue_chunk(a.slab, range.x, n, 1, sm[1], &full[1]);
-  }
+  ring.prologue();
 
   bool done = !inside;
   float T = 1.f, Cr = 0.f, Cg = 0.f, Cb = 0.f;
@@ -94,7 +162,7 @@ __global__ void __launch_bounds__(256) k_render_fwd(RenderArgs a) {
 
   for (uint32_t c = 0; c < nchunks; c++) {
     const int s = c & 1;
-    mbar_wait(&full[s], (c >> 1) & 1);
+    ring.wait(c);
     const uint32_t cnt = min((uint32_t)CH, n - c * CH);
     const float4* st = sm[s];
     for (uint32_t base = 0; base < cnt; base += 32) {
@@ -131,12 +199,12 @@ __global__ void __launch_bounds__(256) k_render_fwd(RenderArgs a) {
     }
     const int num_done = __syncthreads_count(done);
     if (num_done == 256) {
-      // a prefetched chunk may still be in flight into our shared memory: drain before exit
-      if (tid == 0 && c + 1 < nchunks) mbar_wait(&full[(c + 1) & 1], ((c + 1) >> 1) & 1);
+      ring.drain(c);   // a prefetched chunk may still be in flight into our shared memory
       break;
     }
-    if (tid == 0 && c + 2 < nchunks) issue_chunk(a.slab, range.x, n, c + 2, sm[s], &full[s]);
+    ring.refill(c);
   }
+  if (MODE == GATHER_LDGSTS) cp_async_wait<0>();
 
   if (inside) {
     const size_t pid = (size_t)py * a.W + px;
@@ -185,6 +253,7 @@ __device__ __forceinline__ void warp_reduce9(float (&v)[8], float& v8, int lane)
 //   dL/dalpha_j = T_j * <c_j, g> - (<S_j, g> + T_final * <bg, g>) / (1 - alpha_j),   g = dL/dpixel
 // which is algebraically the back-to-front recursion of the public algorithm.
 // ==================================================================================================
+template <int MODE>
 __global__ void __launch_bounds__(256) k_render_bwd(RenderBwdArgs a) {
   __shared__ __align__(128) float4 sm[STAGES][CH * REC_F4];
   __shared__ __align__(8) uint64_t full[STAGES];
@@ -193,6 +262,7 @@ __global__ void __launch_bounds__(256) k_render_bwd(RenderBwdArgs a) {
   const uint2 range = a.ranges[blockIdx.y * gridDim.x + blockIdx.x];
   const uint32_t n = range.y - range.x;
   const uint32_t nchunks = (n + CH - 1) / CH;
+  GatherRing<MODE> ring{sm, full, a.point_list + range.x, a.rec, n, nchunks, 0u, tid};
 
   const int bx = blockIdx.x * TILE + (warp & 1) * 8, by = blockIdx.y * TILE + (warp >> 1) * 4;
   const int px = bx + (lane & 7), py = by + (lane >> 3);
@@ -201,16 +271,7 @@ __global__ void __launch_bounds__(256) k_render_bwd(RenderBwdArgs a) {
   const float rx0 = (float)bx, ry0 = (float)by;
   const float rx1 = (float)min(bx + 7, a.W - 1), ry1 = (float)min(by + 3, a.H - 1);
 
-  if (tid == 0) {
-    mbar_init(&full[0], 1);
-    mbar_init(&full[1], 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
-  if (tid == 0) {
-    if (nchunks > 0) issue_chunk(a.slab, range.x, n, 0, sm[0], &full[0]);
-    if (nchunks > 1) issue_chunk(a.slab, range.x, n, 1, sm[1], &full[1]);
-  }
+  ring.prologue();
 
   float4 fin = make_float4(0.f, 0.f, 0.f, 1.f);
   uint32_t ncontrib = 0;
@@ -231,7 +292,7 @@ __global__ void __launch_bounds__(256) k_render_bwd(RenderBwdArgs a) {
 
   for (uint32_t c = 0; c < nchunks; c++) {
     const int s = c & 1;
-    mbar_wait(&full[s], (c >> 1) & 1);
+    ring.wait(c);
     const uint32_t cnt = min((uint32_t)CH, n - c * CH);
     const float4* st = sm[s];
     for (uint32_t base = 0; base < cnt; base += 32) {
@@ -289,22 +350,33 @@ __global__ void __launch_bounds__(256) k_render_bwd(RenderBwdArgs a) {
     }
     const int num_done = __syncthreads_count(c * CH + cnt >= ncontrib);
     if (num_done == 256) {
-      if (tid == 0 && c + 1 < nchunks) mbar_wait(&full[(c + 1) & 1], ((c + 1) >> 1) & 1);
+      ring.drain(c);
       break;
     }
-    if (tid == 0 && c + 2 < nchunks) issue_chunk(a.slab, range.x, n, c + 2, sm[s], &full[s]);
+    ring.refill(c);
   }
+  if (MODE == GATHER_LDGSTS) cp_async_wait<0>();
+}
+
+static int gather_mode() {
+  static const int mode = [] {
+    const char* e = getenv("B200GS_GATHER");
+    return (e && e[0] == 'l') ? (int)GATHER_LDGSTS : (int)GATHER_TMA;
+  }();
+  return mode;
 }
 
 void launch_render(const RenderArgs& a, cudaStream_t st) {
   const dim3 grid((a.W + TILE - 1) / TILE, (a.H + TILE - 1) / TILE), block(256);
-  k_render_fwd<<<grid, block, 0, st>>>(a);
+  if (gather_mode() == GATHER_TMA) k_render_fwd<GATHER_TMA><<<grid, block, 0, st>>>(a);
+  else k_render_fwd<GATHER_LDGSTS><<<grid, block, 0, st>>>(a);
   count_launch();
 }
 
 void launch_render_bwd(const RenderBwdArgs& a, cudaStream_t st) {
   const dim3 grid((a.W + TILE - 1) / TILE, (a.H + TILE - 1) / TILE), block(256);
-  k_render_bwd<<<grid, block, 0, st>>>(a);
+  if (gather_mode() == GATHER_TMA) k_render_bwd<GATHER_TMA><<<grid, block, 0, st>>>(a);
+  else k_render_bwd<GATHER_LDGSTS><<<grid, block, 0, st>>>(a);
   count_launch();
 }
 

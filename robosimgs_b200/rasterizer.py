@@ -58,22 +58,85 @@ def _f32c(t: Optional[torch.Tensor], name: str, device) -> Optional[torch.Tensor
     return t.contiguous()
 
 
-class _ByteBuffer:
-    """Caller-owned growable scratch buffer handed to the library as a B200GSAlloc."""
+class _ScratchPool:
+    """Per (device, stream) free-lists of byte tensors for the library's scratch buffers.
 
-    def __init__(self, device):
-        self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
-        self._cb = _cabi.RESIZE_FN(self._resize)
-        self.alloc = _cabi.B200GSAlloc(None, self._cb)
+    The scratch sizes vary from frame to frame (they follow the pair count D); routing them through
+    torch's caching allocator makes it split/merge large blocks for dozens of iterations (observed:
+    60 cudaMallocs and 14 GB reserved before it settles).  Buffers are instead leased for the life
+    of one forward call -- or of its autograd node when gradients are needed -- and handed back
+    afterwards; reuse on the same stream is ordered by the stream itself."""
 
-    def _resize(self, _ctx, nbytes):
-        if self.tensor.numel() < nbytes:
-            # round up to 4 significant bits so frame-to-frame size changes hit the same cached
-            # block of torch's allocator instead of a fresh cudaMalloc
-            n = int(nbytes)
-            g = 1 << max(n.bit_length() - 4, 9)
-            self.tensor = torch.empty((n + g - 1) // g * g, dtype=torch.uint8, device=self.tensor.device)
-        return self.tensor.data_ptr()
+    def __init__(self):
+        self.free: dict = {}
+
+    @staticmethod
+    def _round(n: int) -> int:
+        g = 1 << max(int(n).bit_length() - 3, 12)      # keep 3 significant bits of head-room
+        return (int(n) + g - 1) // g * g
+
+    def acquire(self, key, nbytes: int, device) -> torch.Tensor:
+        lst = self.free.setdefault(key, [])
+        best = None
+        for i, t in enumerate(lst):
+            if t.numel() >= nbytes and (best is None or t.numel() < lst[best].numel()):
+                best = i
+        if best is not None:
+            return lst.pop(best)
+        if lst:                                          # grow: drop the largest too-small buffer
+            lst.pop(max(range(len(lst)), key=lambda i: lst[i].numel()))
+        return torch.empty(self._round(nbytes), dtype=torch.uint8, device=device)
+
+    def release(self, key, t: torch.Tensor) -> None:
+        self.free.setdefault(key, []).append(t)
+
+    def clear(self) -> None:
+        self.free.clear()
+
+
+_POOL = _ScratchPool()
+
+
+class _Lease:
+    """Scratch buffers of one forward (or backward) call, handed to the library as B200GSAlloc
+    resize callbacks (the public binding's resizeFunctional).  The callbacks close over a plain
+    dict, not over the lease, so there is no reference cycle: dropping the last reference (e.g. the
+    autograd node dying) returns the buffers to the pool immediately."""
+
+    def __init__(self, device, kinds):
+        self.device = device
+        self.stream = torch.cuda.current_stream(device).cuda_stream
+        self.tensors = tensors = {}
+        keys = {k: (device.index, self.stream, k) for k in kinds}
+        self._keys = keys
+
+        def make(kind):
+            def resize(_ctx, nbytes):
+                t = tensors.get(kind)
+                if t is None or t.numel() < nbytes:
+                    if t is not None:
+                        _POOL.release(keys[kind], t)
+                    t = tensors[kind] = _POOL.acquire(keys[kind], int(nbytes), device)
+                return t.data_ptr()
+            return _cabi.RESIZE_FN(resize)
+
+        self._cbs = {k: make(k) for k in kinds}
+        self.allocs = {k: _cabi.B200GSAlloc(None, cb) for k, cb in self._cbs.items()}
+
+    def tensor(self, kind) -> torch.Tensor:
+        t = self.tensors.get(kind)
+        return t if t is not None else torch.empty(0, dtype=torch.uint8, device=self.device)
+
+    def release(self) -> None:
+        for kind, t in self.tensors.items():
+            _POOL.release(self._keys[kind], t)
+        self.tensors.clear()
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
 
 
 # Pair-capacity hints (see B200GSParams.pair_capacity_hint): the number of (Gaussian,tile) pairs of
@@ -92,7 +155,7 @@ def _params(P, M, rs: GaussianRasterizationSettings, hint: int = 0) -> _cabi.B20
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
-                cov3Ds_precomp, raster_settings):
+                cov3Ds_precomp, raster_settings, grad_mode=True):
         L = _cabi.lib()
         rs = raster_settings
         if getattr(rs, "antialiasing", False):
@@ -120,26 +183,30 @@ class _RasterizeGaussians(torch.autograd.Function):
         prm = _params(P, M, rs, last_D + (last_D >> 4) + 32768 if last_D > 0 else 0)
         color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
         radii = torch.empty((P,), dtype=torch.int32, device=dev)
-        geom, binning, img = _ByteBuffer(dev), _ByteBuffer(dev), _ByteBuffer(dev)
         num_rendered = C.c_int32(0)
         with torch.cuda.device(dev):
-            stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            lease = _Lease(dev, ("geom", "binning", "img"))
+            stream = C.c_void_p(lease.stream)
             _cabi.check(L.b200gs_forward(
                 C.byref(prm), _ptr(bg), _ptr(view), _ptr(proj), _ptr(campos), _ptr(means3D), _ptr(sh),
                 _ptr(colors_precomp), _ptr(opacities), _ptr(scales), _ptr(rotations),
-                _ptr(cov3Ds_precomp), _ptr(color), _ptr(radii), geom.alloc, binning.alloc, img.alloc,
-                C.byref(num_rendered), stream))
+                _ptr(cov3Ds_precomp), _ptr(color), _ptr(radii), lease.allocs["geom"], lease.allocs["binning"],
+                lease.allocs["img"], C.byref(num_rendered), stream))
         ctx.raster_settings = rs
         ctx.num_rendered = int(num_rendered.value)
         _PAIR_HINTS[hint_key] = ctx.num_rendered
         ctx.M = M
         ctx.present = (sh is not None, colors_precomp is not None, scales is not None,
                        cov3Ds_precomp is not None)
-        z = means3D.new_empty(0)
-        ctx.save_for_backward(means3D, z if sh is None else sh, z if colors_precomp is None else colors_precomp,
-                              opacities, z if scales is None else scales, z if rotations is None else rotations,
-                              z if cov3Ds_precomp is None else cov3Ds_precomp, radii, geom.tensor,
-                              binning.tensor, img.tensor, bg, view, proj, campos)
+        if grad_mode and any(ctx.needs_input_grad):
+            z = means3D.new_empty(0)
+            ctx.lease = lease      # scratch stays leased until the autograd node dies
+            ctx.save_for_backward(means3D, z if sh is None else sh, z if colors_precomp is None else colors_precomp,
+                                  opacities, z if scales is None else scales, z if rotations is None else rotations,
+                                  z if cov3Ds_precomp is None else cov3Ds_precomp, radii, lease.tensor("geom"),
+                                  lease.tensor("binning"), lease.tensor("img"), bg, view, proj, campos)
+        else:
+            lease.release()        # forward-only: the next call on this stream may reuse the scratch
         ctx.mark_non_differentiable(radii)
         return color, radii
 
@@ -166,25 +233,26 @@ class _RasterizeGaussians(torch.autograd.Function):
         g_rots = e(P, 4) if has_sr else None
         g_cov = e(P, 6) if has_cov else None
         prm = _params(P, ctx.M, rs)
-        scratch = _ByteBuffer(dev)
         with torch.cuda.device(dev):
-            stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            lease = _Lease(dev, ("scratch",))
+            stream = C.c_void_p(lease.stream)
             _cabi.check(L.b200gs_backward(
                 C.byref(prm), _ptr(bg), _ptr(view), _ptr(proj), _ptr(campos), _ptr(means3D), _ptr(sh),
                 _ptr(colors_precomp), _ptr(opacities), _ptr(scales), _ptr(rotations),
                 _ptr(cov3Ds_precomp), _ptr(radii), _ptr(geom), _ptr(binning), _ptr(img),
                 C.c_int32(ctx.num_rendered), _ptr(grad_out_color), _ptr(g_means3D), _ptr(g_means2D),
                 _ptr(g_sh), _ptr(g_col), _ptr(g_opac), _ptr(g_scales), _ptr(g_rots), _ptr(g_cov),
-                scratch.alloc, stream))
+                lease.allocs["scratch"], stream))
+            lease.release()
         # order of the public interface: means3D, means2D, sh, colors_precomp, opacities, scales,
         # rotations, cov3Ds_precomp, raster_settings
-        return g_means3D, g_means2D, g_sh, g_col, g_opac, g_scales, g_rots, g_cov, None
+        return g_means3D, g_means2D, g_sh, g_col, g_opac, g_scales, g_rots, g_cov, None, None
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
                         cov3Ds_precomp, raster_settings):
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
-                                     cov3Ds_precomp, raster_settings)
+                                     cov3Ds_precomp, raster_settings, torch.is_grad_enabled())
 
 
 class GaussianRasterizer(nn.Module):
