@@ -406,7 +406,7 @@ int b200gs_backward(const B200GSParams* prm, const float* bg, const float* viewm
   pa.tanfovx = prm->tanfovx; pa.tanfovy = prm->tanfovy; pa.scale_modifier = prm->scale_modifier;
   pa.means = means3D; pa.scales = scales; pa.rots = rotations; pa.shs = shs; pa.cov3d_precomp = cov3D_precomp;
   pa.view = viewmatrix; pa.proj = projmatrix; pa.campos = campos;
-  pa.radii = radii; pa.tiles = gb.tiles; pa.clamped = gb.clamped; pa.grad2d = grad2d;
+  pa.radii = radii; pa.tiles = gb.tiles; pa.clamped = gb.clamped; pa.rec = gb.rec; pa.grad2d = grad2d;
   pa.dL_dmeans = dL_dmeans3D; pa.dL_dmeans2D = dL_dmeans2D; pa.dL_dshs = dL_dshs; pa.dL_dcolors = dL_dcolors_precomp;
   pa.dL_dopac = dL_dopacities; pa.dL_dscales = dL_dscales; pa.dL_drots = dL_drotations; pa.dL_dcov3D = dL_dcov3D;
   {

@@ -65,6 +65,7 @@ struct ProjectBwdArgs {
   const int32_t* radii;
   const uint32_t* tiles;
   const uint8_t* clamped;
+  const float4* rec;
   const float* grad2d;
   float *dL_dmeans, *dL_dmeans2D, *dL_dshs, *dL_dcolors, *dL_dopac, *dL_dscales, *dL_drots, *dL_dcov3D;
 };

@@ -169,62 +169,70 @@ __device__ __forceinline__ TileRect reference_rect(float px, float py, int radiu
   return r;
 }
 
+// All span arithmetic uses explicitly rounded intrinsics / fixed PTX approximations, so the count
+// (k_project) and the emission (k_emit_*) see bit-identical spans wherever the code is inlined.
+__device__ __forceinline__ float sqrt_approx(float v) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+
 struct SpanCtx {
-  float x, y, A, B, C;
-  float tau;        // 2*thr
+  float x, y, B;
+  float A_tau;      // A * tau, tau = 2*thr
   float inv_A;
   float det;        // A*C - B*B
   float x_ext;      // half-extent of the ellipse in x
   float y_at_xext;  // dy at the right-most point of the ellipse
   float y_ext;
+  float pad;
+  int ty0, ty1;     // tile rows the ellipse can reach, clipped to the reference rect
 };
 
 __device__ __forceinline__ bool span_setup(SpanCtx& s, float x, float y, float A, float B, float C,
-                                           float thr) {
-  s.x = x; s.y = y; s.A = A; s.B = B; s.C = C;
-  s.tau = __fmul_rn(2.f, thr);
+                                           float thr, const TileRect& r) {
+  s.x = x; s.y = y; s.B = B;
+  const float tau = __fmul_rn(2.f, thr);
   s.det = __fmaf_rn(A, C, -__fmul_rn(B, B));
+  s.ty0 = s.ty1 = 0;
   if (!(thr > 0.f) || !(s.det > 0.f) || !(A > 0.f) || !(C > 0.f)) return false;
+  s.A_tau = __fmul_rn(A, tau);
   s.inv_A = __frcp_rn(A);
-  s.x_ext = __fsqrt_rn(__fdiv_rn(__fmul_rn(s.tau, C), s.det));
-  s.y_ext = __fsqrt_rn(__fdiv_rn(__fmul_rn(s.tau, A), s.det));
-  s.y_at_xext = -__fdiv_rn(__fmul_rn(B, s.x_ext), C);
-  return true;
+  const float inv_det = __frcp_rn(s.det);
+  // 0.5% + 0.02 px outward padding absorbs the approximations below
+  s.x_ext = __fmaf_rn(sqrt_approx(__fmul_rn(__fmul_rn(tau, C), inv_det)), 1.005f, 0.02f);
+  s.y_ext = __fmaf_rn(sqrt_approx(__fmul_rn(__fmul_rn(tau, A), inv_det)), 1.005f, 0.02f);
+  s.y_at_xext = -__fmul_rn(__fmul_rn(B, s.x_ext), __frcp_rn(C));
+  s.pad = __fmaf_rn(0.01f, s.x_ext, 0.02f);
+  // tile row ty holds pixel-centre rows [16 ty, 16 ty + 15]
+  const int lo = (int)ceilf(__fmul_rn(__fadd_rn(__fadd_rn(y, -s.y_ext), -(float)(TILE - 1)), 1.f / TILE));
+  const int hi = (int)floorf(__fmul_rn(__fadd_rn(y, s.y_ext), 1.f / TILE)) + 1;
+  s.ty0 = max(r.y0, lo);
+  s.ty1 = min(r.y1, hi);
+  return s.ty1 > s.ty0;
 }
 
-// x-interval (relative to the centre) of the ellipse {A dx^2 + 2B dx dy + C dy^2 <= tau} inside the
-// band dy in [a,b]; returns false if the band misses the ellipse.  1% outward padding on the
-// half-widths absorbs rounding.
-__device__ __noinline__ bool band_x_extent(const SpanCtx& s, float a, float b, float& lo, float& hi) {
+// tile-column span [c0,c1) of tile row ty: x-interval of the ellipse {A dx^2 + 2B dx dy + C dy^2 <=
+// tau} inside the band of pixel-centre rows [16 ty, 16 ty + 15], clipped to the reference rect.
+__device__ __forceinline__ void row_span(const SpanCtx& s, const TileRect& r, int ty, int& c0, int& c1) {
+  c0 = c1 = 0;
+  float a = __fadd_rn((float)(ty * TILE) - 0.02f, -s.y);
+  float b = __fadd_rn((float)(ty * TILE + TILE - 1) + 0.02f, -s.y);
   a = fmaxf(a, -s.y_ext);
   b = fminf(b, s.y_ext);
-  if (a > b) return false;
+  if (a > b) return;
   // half-width at dy: sqrt(A*tau - det*dy^2)/A ; centre line: -B*dy/A
-  const float da = __fsqrt_rn(fmaxf(0.f, __fmaf_rn(-s.det, __fmul_rn(a, a), __fmul_rn(s.A, s.tau))));
-  const float db = __fsqrt_rn(fmaxf(0.f, __fmaf_rn(-s.det, __fmul_rn(b, b), __fmul_rn(s.A, s.tau))));
+  const float da = sqrt_approx(fmaxf(0.f, __fmaf_rn(-s.det, __fmul_rn(a, a), s.A_tau)));
+  const float db = sqrt_approx(fmaxf(0.f, __fmaf_rn(-s.det, __fmul_rn(b, b), s.A_tau)));
   const float ca = -__fmul_rn(s.B, a), cb = -__fmul_rn(s.B, b);
-  float xmax = fmaxf(__fmul_rn(__fadd_rn(ca, da), s.inv_A), __fmul_rn(__fadd_rn(cb, db), s.inv_A));
-  float xmin = fminf(__fmul_rn(__fadd_rn(ca, -da), s.inv_A), __fmul_rn(__fadd_rn(cb, -db), s.inv_A));
+  float xmax = __fmul_rn(fmaxf(__fadd_rn(ca, da), __fadd_rn(cb, db)), s.inv_A);
+  float xmin = __fmul_rn(fminf(__fadd_rn(ca, -da), __fadd_rn(cb, -db)), s.inv_A);
   if (s.y_at_xext >= a && s.y_at_xext <= b) xmax = s.x_ext;     // right-most point inside the band
   if (-s.y_at_xext >= a && -s.y_at_xext <= b) xmin = -s.x_ext;  // left-most point inside the band
-  const float pad = __fmaf_rn(0.01f, s.x_ext, 0.01f);
-  lo = xmin - pad;
-  hi = xmax + pad;
-  return true;
-}
-
-// tile-column span [c0,c1) of tile row ty, clipped to the reference rect
-__device__ __forceinline__ void row_span(const SpanCtx& s, const TileRect& r, int ty, int& c0, int& c1) {
-  // pixel-centre rows of this tile row: [16 ty, 16 ty + 15] (+- 0.01 px rounding pad)
-  const float a = (float)(ty * TILE) - 0.01f - s.y;
-  const float b = (float)(ty * TILE + TILE - 1) + 0.01f - s.y;
-  float lo, hi;
-  c0 = c1 = 0;
-  if (!band_x_extent(s, a, b, lo, hi)) return;
-  const float X0 = s.x + lo, X1 = s.x + hi;
+  const float X0 = __fadd_rn(s.x, __fadd_rn(xmin, -s.pad)), X1 = __fadd_rn(s.x, __fadd_rn(xmax, s.pad));
   // tile tx holds pixel centres [16 tx, 16 tx + 15]: intersects [X0,X1] iff 16tx <= X1 and 16tx+15 >= X0
-  int t0 = (int)ceilf((X0 - (float)(TILE - 1)) * (1.f / TILE));
-  int t1 = (int)floorf(X1 * (1.f / TILE)) + 1;
+  int t0 = (int)ceilf(__fmul_rn(__fadd_rn(X0, -(float)(TILE - 1)), 1.f / TILE));
+  int t1 = (int)floorf(__fmul_rn(X1, 1.f / TILE)) + 1;
   t0 = max(t0, r.x0);
   t1 = min(t1, r.x1);
   if (t1 > t0) { c0 = t0; c1 = t1; }
@@ -233,9 +241,9 @@ __device__ __forceinline__ void row_span(const SpanCtx& s, const TileRect& r, in
 __device__ __forceinline__ uint32_t count_tiles(float x, float y, float A, float B, float C, float thr,
                                                 const TileRect& r) {
   SpanCtx s;
-  if (!span_setup(s, x, y, A, B, C, thr)) return 0;
+  if (!span_setup(s, x, y, A, B, C, thr, r)) return 0;
   uint32_t n = 0;
-  for (int ty = r.y0; ty < r.y1; ty++) {
+  for (int ty = s.ty0; ty < s.ty1; ty++) {
     int c0, c1;
     row_span(s, r, ty, c0, c1);
     n += (uint32_t)(c1 - c0);
@@ -368,8 +376,8 @@ __global__ void __launch_bounds__(256) k_emit_pairs(EmitArgs a) {
     uint32_t o = off;
     const TileRect rect = reference_rect(q0.x, q0.y, radius, a.gx, a.gy);
     SpanCtx s;
-    if (span_setup(s, q0.x, q0.y, q0.z, q0.w, q1.x, q1.z)) {
-      for (int ty = rect.y0; ty < rect.y1; ty++) {
+    if (span_setup(s, q0.x, q0.y, q0.z, q0.w, q1.x, q1.z, rect)) {
+      for (int ty = s.ty0; ty < s.ty1; ty++) {
         int c0, c1;
         row_span(s, rect, ty, c0, c1);
         for (int tx = c0; tx < c1 && o < end; tx++, o++) {
@@ -417,12 +425,12 @@ __global__ void __launch_bounds__(256) k_emit_big(EmitArgs a) {
     const float4 q0 = a.rec[(size_t)g * REC_F4], q1 = a.rec[(size_t)g * REC_F4 + 1];
     const TileRect rect = reference_rect(q0.x, q0.y, a.radii[g], a.gx, a.gy);
     SpanCtx s;
-    const bool ok = span_setup(s, q0.x, q0.y, q0.z, q0.w, q1.x, q1.z);
+    const bool ok = span_setup(s, q0.x, q0.y, q0.z, q0.w, q1.x, q1.z, rect);
     uint32_t o = off;
-    for (int y_base = rect.y0; ok && y_base < rect.y1; y_base += 32) {
+    for (int y_base = s.ty0; ok && y_base < s.ty1; y_base += 32) {
       const int ty = y_base + lane;
       int c0 = 0, c1 = 0;
-      if (ty < rect.y1) row_span(s, rect, ty, c0, c1);
+      if (ty < s.ty1) row_span(s, rect, ty, c0, c1);
       const uint32_t len = (uint32_t)(c1 - c0);
       uint32_t incl = len;
 #pragma unroll
@@ -431,7 +439,7 @@ __global__ void __launch_bounds__(256) k_emit_big(EmitArgs a) {
         if (lane >= d) incl += t;
       }
       const uint32_t row_off = o + incl - len;
-      const int rows = min(32, rect.y1 - y_base);
+      const int rows = min(32, s.ty1 - y_base);
       for (int i = 0; i < rows; i++) {
         const uint32_t l_i = __shfl_sync(0xffffffffu, len, i);
         if (l_i == 0) continue;
@@ -480,8 +488,11 @@ __global__ void k_mark_visible(int P, const float* __restrict__ means, const flo
 
 // ==================================================================================================
 // K8 + K9 fused: adjoint of the projection, SH colour and Sigma3D for one Gaussian per thread.
-// Reads the screen-space accumulator grad2d[P][12] = {dcol r,g,b, dopacity, dmean2D x,y (NDC-scaled),
-// dA, dB, dC, -, -, -} written by the compositing adjoint.  Every output element is written.
+// Reads the screen-space accumulator grad2d[P][12] = {dcol r,g,b, S0, Sx, Sy, Sxx, Sxy, Syy, -, -, -}
+// written by the compositing adjoint: moments of m = G * dL/dalpha about the splat centre, from which
+//   dL/dopacity = S0,  dL/dmean2D = -o (A Sx + B Sy, C Sy + B Sx) * (0.5 W, 0.5 H)   (NDC-scaled),
+//   dL/dA = -0.5 o Sxx,  dL/dB = -o Sxy,  dL/dC = -0.5 o Syy.
+// Every output element is written.
 // ==================================================================================================
 template <int DEG>
 __global__ void __launch_bounds__(256) k_project_bwd(ProjectBwdArgs a) {
@@ -505,8 +516,12 @@ __global__ void __launch_bounds__(256) k_project_bwd(ProjectBwdArgs a) {
     const float4 ga4 = g4[0], gb4 = g4[1], gc4 = g4[2];
     gcol[0] = ga4.x; gcol[1] = ga4.y; gcol[2] = ga4.z;
     gop = ga4.w;
-    g2x = gb4.x; g2y = gb4.y;
-    const float gA = gb4.z, gB = gb4.w, gC = gc4.x;
+    const float4 r0 = a.rec[(size_t)i * REC_F4], r1 = a.rec[(size_t)i * REC_F4 + 1];
+    const float cA = r0.z, cB = r0.w, cC = r1.x, op = r1.y;
+    const float Sx = gb4.x, Sy = gb4.y, Sxx = gb4.z, Sxy = gb4.w, Syy = gc4.x;
+    g2x = -op * (cA * Sx + cB * Sy) * (0.5f * (float)a.W);
+    g2y = -op * (cC * Sy + cB * Sx) * (0.5f * (float)a.H);
+    const float gA = -0.5f * op * Sxx, gB = -op * Sxy, gC = -0.5f * op * Syy;
 
     const float3 mu = make_float3(__ldg(a.means + 3 * i), __ldg(a.means + 3 * i + 1), __ldg(a.means + 3 * i + 2));
     float c3[6];

@@ -39,10 +39,10 @@ __device__ __forceinline__ bool block_may_contribute(float x, float y, float A, 
   const float cx = clampf(x, x0, x1), cy = clampf(y, y0, y1);
   const float dxe = cx - x, dye = cy - y;
   // vertical edge X = cx: minimise over Y
-  float dy1 = clampf(y - B * dxe / C, y0, y1) - y;
+  float dy1 = clampf(y - __fdividef(B * dxe, C), y0, y1) - y;
   const float q1 = A * dxe * dxe + 2.f * B * dxe * dy1 + C * dy1 * dy1;
   // horizontal edge Y = cy: minimise over X
-  float dx2 = clampf(x - B * dye / A, x0, x1) - x;
+  float dx2 = clampf(x - __fdividef(B * dye, A), x0, x1) - x;
   const float q2 = A * dx2 * dx2 + 2.f * B * dx2 * dye + C * dye * dye;
   const float q = fminf(q1, q2);
   // rounding guard: relative to the magnitude of the cancelling terms
@@ -287,7 +287,6 @@ __global__ void __launch_bounds__(256) k_render_bwd(RenderBwdArgs a) {
   }
   // T_final * <bg, g>
   const float bgterm = fin.w * (__ldg(a.bg) * gr + __ldg(a.bg + 1) * gg + __ldg(a.bg + 2) * gb);
-  const float halfW = 0.5f * (float)a.W, halfH = 0.5f * (float)a.H;
   float T = 1.f, Cr = 0.f, Cg = 0.f, Cb = 0.f;
 
   for (uint32_t c = 0; c < nchunks; c++) {
@@ -322,18 +321,22 @@ __global__ void __launch_bounds__(256) k_render_bwd(RenderBwdArgs a) {
           Cr = __fmaf_rn(q2.x, w, Cr);
           Cg = __fmaf_rn(q2.y, w, Cg);
           Cb = __fmaf_rn(q2.z, w, Cb);
-          const float inv1ma = 1.f / (1.f - alpha);
+          const float inv1ma = __fdividef(1.f, 1.f - alpha);
           const float behind = (fin.x - Cr) * gr + (fin.y - Cg) * gg + (fin.z - Cb) * gb;
           const float dL_dalpha = T * (q2.x * gr + q2.y * gg + q2.z * gb) - inv1ma * (behind + bgterm);
           T = T * (1.f - alpha);
-          const float gv = q1.y * G * dL_dalpha;          // dL/dG * G
+          // Per-splat factors (opacity, conic, 0.5*W/H) are uniform over the pixels, so only the raw
+          // moments of m = G * dL/dalpha about the splat centre are reduced; k_project_bwd turns them
+          // into dL/d{opacity, mean2D, conic}.
+          const float m = G * dL_dalpha;
+          const float mx = m * dx, my = m * dy;
           v[0] = w * gr; v[1] = w * gg; v[2] = w * gb;     // dL/dcolour
-          v[3] = G * dL_dalpha;                            // dL/dopacity
-          v[4] = -gv * (q0.z * dx + q0.w * dy) * halfW;    // dL/dmean2D.x (NDC-scaled)
-          v[5] = -gv * (q1.x * dy + q0.w * dx) * halfH;    // dL/dmean2D.y
-          v[6] = -0.5f * gv * dx * dx;                     // dL/dA
-          v[7] = -gv * dx * dy;                            // dL/dB
-          v8 = -0.5f * gv * dy * dy;                       // dL/dC
+          v[3] = m;                                        // S0  (= dL/dopacity)
+          v[4] = mx;                                       // Sx
+          v[5] = my;                                       // Sy
+          v[6] = mx * dx;                                  // Sxx
+          v[7] = mx * dy;                                  // Sxy
+          v8 = my * dy;                                    // Syy
         } else {
 #pragma unroll
           for (int k = 0; k < 8; k++) v[k] = 0.f;
@@ -361,7 +364,7 @@ __global__ void __launch_bounds__(256) k_render_bwd(RenderBwdArgs a) {
 static int gather_mode() {
   static const int mode = [] {
     const char* e = getenv("B200GS_GATHER");
-    return (e && e[0] == 'l') ? (int)GATHER_LDGSTS : (int)GATHER_TMA;
+    return (e && e[0] == 't') ? (int)GATHER_TMA : (int)GATHER_LDGSTS;
   }();
   return mode;
 }
