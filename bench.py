@@ -113,10 +113,10 @@ def algorithmic_bytes(P, P_vis, D, M):
     px = W_IMG * H_IMG
     per_stage = {
         "project": P * b_in + P_vis * 48,
-        "depth_sort_scan": P * 8 * 2 + P * 8,
-        "emit_pairs": D * 8,
-        "tile_sort": D * 8 * 2,
-        "tile_ranges": D * 4,
+        "scan": P * 8,
+        "emit_pairs": D * 12,
+        "pair_sort": D * 12 * 2,
+        "tile_ranges": D * 8,
         "render": D * 40 + px * (12 + 8),
         "render_bwd": D * 40 + px * (12 + 8) + P_vis * 40,
         "project_bwd": P_vis * 40 + P * b_in + P * (b_in + 12),

@@ -2,6 +2,7 @@
 // forward / backward launch sequences.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <atomic>
 #include <mutex>
@@ -34,7 +35,7 @@ int debug_sync(const B200GSParams* prm, cudaStream_t s, const char* what) {
 }
 
 // ---- optional per-stage device timing (bench / roofline accounting) ----------------------------
-static const char* kStageNames[B200GS_NUM_STAGES] = {"project", "depth_sort_scan", "emit_pairs", "tile_sort",
+static const char* kStageNames[B200GS_NUM_STAGES] = {"project", "scan", "emit_pairs", "pair_sort",
                                                      "tile_ranges", "render", "render_bwd", "project_bwd"};
 struct StageSpan { int stage; cudaEvent_t a, b; };
 static std::mutex g_prof_mu;
@@ -64,6 +65,22 @@ struct StageTimer {
   }
 };
 
+// log2(bin edge / 16): pairs are binned per (16 << shift)^2 pixels (see project.cu:bin_rect).
+// Default: the smallest shift that leaves at most 255 bins (bin id fits 8 key bits -> 40-bit sort
+// keys), capped at 3 (64 compositing CTAs share one bin list).  B200GS_BIN_SHIFT overrides.
+static int bin_shift_for(int gx, int gy) {
+  static const int forced = [] {
+    const char* e = getenv("B200GS_BIN_SHIFT");
+    if (!e) return -1;
+    const int s = atoi(e);
+    return s < 0 ? 0 : (s > 5 ? 5 : s);
+  }();
+  if (forced >= 0) return forced;
+  int s = 0;
+  while (s < 3 && (((gx + (1 << s) - 1) >> s) * ((gy + (1 << s) - 1) >> s)) > 255) s++;
+  return s;
+}
+
 static int tile_bits_for(int num_tiles) {
   int bits = 1;
   while ((1 << bits) <= num_tiles) bits++;  // room for the invalid id == num_tiles
@@ -75,14 +92,12 @@ static GeomBuf carve_geom(char* base, int P, size_t* bytes) {
   GeomBuf g;
   g.rec = c.take<float4>((size_t)P * REC_F4);
   g.depth_key = c.take<uint32_t>(P);
-  g.idx = c.take<uint32_t>(P);
-  g.key_sorted = c.take<uint32_t>(P);
-  g.perm = c.take<uint32_t>(P);
+  g.big_queue = c.take<uint32_t>(P);
   g.tiles = c.take<uint32_t>(P);
   g.offsets = c.take<uint32_t>(P);
   g.clamped = c.take<uint8_t>(P);
   g.counters = c.take<uint32_t>(32);
-  g.cub_temp_bytes = depth_sort_temp_bytes(P);
+  g.cub_temp_bytes = scan_temp_bytes(P);
   g.cub_temp = c.take<char>(g.cub_temp_bytes);
   if (bytes) *bytes = c.bytes();
   return g;
@@ -92,10 +107,10 @@ static BinBuf carve_binning(char* base, int64_t D, int tile_bits, size_t* bytes)
   Carver c(base);
   BinBuf b;
   b.vals_sorted = c.take<uint32_t>(D);
-  b.keys_sorted = c.take<uint32_t>(D);
-  b.keys = c.take<uint32_t>(D);
+  b.keys_sorted = c.take<uint64_t>(D);
+  b.keys = c.take<uint64_t>(D);
   b.vals = c.take<uint32_t>(D);
-  b.cub_temp_bytes = tile_sort_temp_bytes(D, tile_bits);
+  b.cub_temp_bytes = pair_sort_temp_bytes(D, 32 + tile_bits);
   b.cub_temp = c.take<char>(b.cub_temp_bytes);
   if (bytes) *bytes = c.bytes();
   return b;
@@ -211,7 +226,9 @@ int b200gs_profile_read(float* stage_ms, int32_t* stage_calls, int reset) {
 int b200gs_buffer_sizes(int32_t P, int32_t H, int32_t W, int64_t D, size_t* geom_bytes,
                         size_t* binning_bytes, size_t* img_bytes) {
   if (P < 0 || H <= 0 || W <= 0 || D < 0) { set_error("invalid sizes"); return B200GS_ERR_INVALID_ARG; }
-  const int num_tiles = ((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+  const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+  const int bs = bin_shift_for(gx, gy);
+  const int num_tiles = ((gx + (1 << bs) - 1) >> bs) * ((gy + (1 << bs) - 1) >> bs);
   if (geom_bytes) carve_geom(nullptr, P, geom_bytes);
   if (binning_bytes) carve_binning(nullptr, D, tile_bits_for(num_tiles), binning_bytes);
   if (img_bytes) carve_img(nullptr, H, W, img_bytes);
@@ -235,7 +252,9 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int P = prm->P, H = prm->image_height, W = prm->image_width;
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
-  const int num_tiles = gx * gy;
+  const int bs = bin_shift_for(gx, gy);
+  const int gbx = (gx + (1 << bs) - 1) >> bs, gby = (gy + (1 << bs) - 1) >> bs;
+  const int num_tiles = gbx * gby;   // bins
   const int tile_bits = tile_bits_for(num_tiles);
 
   size_t geom_bytes, img_bytes;
@@ -248,13 +267,13 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
   ImgBuf ib = carve_img(img_p, H, W, nullptr);
 
   ProjectArgs pa;
-  pa.P = P; pa.M = prm->M; pa.W = W; pa.H = H; pa.gx = gx; pa.gy = gy;
+  pa.P = P; pa.M = prm->M; pa.W = W; pa.H = H; pa.gx = gx; pa.gy = gy; pa.bin_shift = bs;
   pa.sh_vec = (shs && (prm->M & 3) == 0 && (reinterpret_cast<uintptr_t>(shs) & 15) == 0) ? 1 : 0;
   pa.tanfovx = prm->tanfovx; pa.tanfovy = prm->tanfovy; pa.scale_modifier = prm->scale_modifier;
   pa.means = means3D; pa.scales = scales; pa.rots = rotations; pa.opac = opacities; pa.shs = shs;
   pa.colors_precomp = colors_precomp; pa.cov3d_precomp = cov3D_precomp;
   pa.view = viewmatrix; pa.proj = projmatrix; pa.campos = campos;
-  pa.radii = radii; pa.rec = gb.rec; pa.depth_key = gb.depth_key; pa.idx = gb.idx; pa.tiles = gb.tiles;
+  pa.radii = radii; pa.rec = gb.rec; pa.depth_key = gb.depth_key; pa.tiles = gb.tiles;
   pa.clamped = gb.clamped;
   {
     StageTimer t(0, st);
@@ -263,9 +282,9 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
   if ((rc = debug_sync(prm, st, "project"))) return rc;
   {
     StageTimer t(1, st);
-    if ((rc = sort_by_depth_and_scan(gb, P, st))) return rc;
+    if ((rc = scan_bin_counts(gb, P, st))) return rc;
   }
-  if ((rc = debug_sync(prm, st, "depth sort + scan"))) return rc;
+  if ((rc = debug_sync(prm, st, "scan"))) return rc;
 
   // ---- binning + compositing for a given pair capacity (D <= cap slots; [D,cap) are padding) ----
   auto run_binning_and_render = [&](uint32_t cap) -> int {
@@ -280,10 +299,11 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
     if (cap > 0) {
       if ((rc2 = check_cuda(cudaMemsetAsync(gb.counters, 0, 32 * sizeof(uint32_t), st), "clear counters"))) return rc2;
       EmitArgs ea;
-      ea.P = P; ea.gx = gx; ea.gy = gy; ea.invalid_tile = (uint32_t)num_tiles; ea.capacity = cap;
-      ea.perm = gb.perm; ea.tiles = gb.tiles; ea.offsets = gb.offsets; ea.rec = gb.rec; ea.radii = radii;
+      ea.P = P; ea.gx = gx; ea.gy = gy; ea.gbx = gbx; ea.bin_shift = bs;
+      ea.invalid_tile = (uint32_t)num_tiles; ea.capacity = cap;
+      ea.tiles = gb.tiles; ea.offsets = gb.offsets; ea.depth_key = gb.depth_key; ea.rec = gb.rec; ea.radii = radii;
       ea.keys = bb.keys; ea.vals = bb.vals;
-      ea.big_queue = gb.key_sorted; ea.big_count = gb.counters;
+      ea.big_queue = gb.big_queue; ea.big_count = gb.counters;
       {
         StageTimer t(2, st);
         launch_emit_pairs(ea, st);
@@ -291,9 +311,9 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
       if ((rc2 = debug_sync(prm, st, "emit pairs"))) return rc2;
       {
         StageTimer t(3, st);
-        if ((rc2 = sort_by_tile(bb, cap, tile_bits, st))) return rc2;
+        if ((rc2 = sort_pairs(bb, cap, 32 + tile_bits, st))) return rc2;
       }
-      if ((rc2 = debug_sync(prm, st, "tile sort"))) return rc2;
+      if ((rc2 = debug_sync(prm, st, "pair sort"))) return rc2;
       RangesArgs ga;
       ga.D = cap; ga.num_tiles = (uint32_t)num_tiles; ga.keys_sorted = bb.keys_sorted; ga.ranges = ib.ranges;
       {
@@ -303,8 +323,8 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
       if ((rc2 = debug_sync(prm, st, "tile ranges"))) return rc2;
     }
     RenderArgs ra;
-    ra.W = W; ra.H = H; ra.ranges = ib.ranges; ra.point_list = bb.vals_sorted; ra.rec = gb.rec; ra.bg = bg;
-    ra.out_color = out_color;
+    ra.W = W; ra.H = H; ra.gbx = gbx; ra.bin_shift = bs; ra.ranges = ib.ranges; ra.point_list = bb.vals_sorted;
+    ra.rec = gb.rec; ra.bg = bg; ra.out_color = out_color;
     ra.pix = ib.pix; ra.n_contrib = ib.n_contrib;
     {
       StageTimer t(5, st);
@@ -376,7 +396,9 @@ int b200gs_backward(const B200GSParams* prm, const float* bg, const float* viewm
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
-  const int tile_bits = tile_bits_for(gx * gy);
+  const int bs = bin_shift_for(gx, gy);
+  const int gbx = (gx + (1 << bs) - 1) >> bs, gby = (gy + (1 << bs) - 1) >> bs;
+  const int tile_bits = tile_bits_for(gbx * gby);
   GeomBuf gb = carve_geom(const_cast<char*>(geom), P, nullptr);
   BinBuf bb = carve_binning(const_cast<char*>(binning), num_rendered, tile_bits, nullptr);
   ImgBuf ib = carve_img(const_cast<char*>(img), H, W, nullptr);
@@ -389,8 +411,8 @@ int b200gs_backward(const B200GSParams* prm, const float* bg, const float* viewm
 
   if (num_rendered > 0) {
     RenderBwdArgs ra;
-    ra.W = W; ra.H = H; ra.ranges = ib.ranges; ra.point_list = bb.vals_sorted; ra.rec = gb.rec; ra.bg = bg;
-    ra.pix = ib.pix;
+    ra.W = W; ra.H = H; ra.gbx = gbx; ra.bin_shift = bs; ra.ranges = ib.ranges; ra.point_list = bb.vals_sorted;
+    ra.rec = gb.rec; ra.bg = bg; ra.pix = ib.pix;
     ra.n_contrib = ib.n_contrib; ra.dL_dpix = dL_dout_color; ra.grad2d = grad2d;
     {
       StageTimer t(6, st);

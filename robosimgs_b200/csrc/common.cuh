@@ -36,12 +36,10 @@ struct Carver {
 
 struct GeomBuf {
   float4* rec;          // [P*3]
-  uint32_t* depth_key;  // [P]
-  uint32_t* idx;        // [P] iota
-  uint32_t* key_sorted; // [P]
-  uint32_t* perm;       // [P] Gaussian indices in depth order
-  uint32_t* tiles;      // [P] tiles touched (tight count)
-  uint32_t* offsets;    // [P] inclusive scan of tiles[perm[i]]
+  uint32_t* depth_key;  // [P] IEEE bits of the view-space depth (positive floats order like uints)
+  uint32_t* big_queue;  // [P] ids of large-footprint Gaussians (emitted one warp each)
+  uint32_t* tiles;      // [P] bins touched (tight count)
+  uint32_t* offsets;    // [P] inclusive scan of tiles[]
   uint8_t* clamped;     // [P] bit c set: colour channel c was clamped at 0
   uint32_t* counters;   // [32] device-side scalars (large-footprint queue length, ...)
   char* cub_temp;
@@ -51,8 +49,8 @@ struct GeomBuf {
 struct BinBuf {
   uint32_t* vals_sorted; // [D] Gaussian ids in (tile, depth) order -- FIRST chunk: the only part the
                          // backward pass reads, so its offset must not depend on the capacity
-  uint32_t* keys_sorted; // [D]
-  uint32_t* keys;        // [D] tile ids, emit order (depth-major)
+  uint64_t* keys_sorted; // [D]
+  uint64_t* keys;        // [D] (bin << 32) | depth bits, emission (index) order
   uint32_t* vals;        // [D] Gaussian ids
   char* cub_temp;
   size_t cub_temp_bytes;

@@ -5,37 +5,39 @@
 namespace b200gs {
 
 struct ProjectArgs {
-  int P, M, W, H, gx, gy, sh_vec;
+  int P, M, W, H, gx, gy, sh_vec, bin_shift;
   float tanfovx, tanfovy, scale_modifier;
   const float *means, *scales, *rots, *opac, *shs, *colors_precomp, *cov3d_precomp;
   const float *view, *proj, *campos;
   int32_t* radii;
   float4* rec;
-  uint32_t *depth_key, *idx, *tiles;
+  uint32_t *depth_key, *tiles;
   uint8_t* clamped;
 };
 
 struct EmitArgs {
-  int P, gx, gy;
+  int P, gx, gy;     // gx, gy: 16-px tile grid (reference rect)
+  int gbx, bin_shift; // bin grid width, log2(bin edge / 16)
   uint32_t invalid_tile;
   uint32_t capacity;   // number of pair slots in keys/vals; slots [D, capacity) are padded
-  const uint32_t *perm, *tiles, *offsets;
+  const uint32_t *tiles, *offsets, *depth_key;
   const float4* rec;
   const int32_t* radii;
-  uint32_t *keys, *vals;
-  uint32_t* big_queue;  // [P] ranks of large-footprint Gaussians (reuses the sorted-key buffer)
+  uint64_t* keys;       // (bin << 32) | depth bits
+  uint32_t* vals;       // Gaussian id
+  uint32_t* big_queue;  // [P] ids of large-footprint Gaussians
   uint32_t* big_count;  // [1] zeroed before the emission stage
 };
 
 struct RangesArgs {
   int64_t D;           // sorted pair slots (incl. padding of the speculative capacity)
   uint32_t num_tiles;
-  const uint32_t* keys_sorted;
+  const uint64_t* keys_sorted;
   uint2* ranges;
 };
 
 struct RenderArgs {
-  int W, H;
+  int W, H, gbx, bin_shift;
   const uint2* ranges;
   const uint32_t* point_list;  // Gaussian ids in (tile, depth) order
   const float4* rec;           // [P] projected-splat records
@@ -46,7 +48,7 @@ struct RenderArgs {
 };
 
 struct RenderBwdArgs {
-  int W, H;
+  int W, H, gbx, bin_shift;
   const uint2* ranges;
   const uint32_t* point_list;
   const float4* rec;
@@ -78,10 +80,10 @@ void launch_project_bwd(const ProjectBwdArgs& a, int deg, cudaStream_t st);
 void launch_render(const RenderArgs& a, cudaStream_t st);
 void launch_render_bwd(const RenderBwdArgs& a, cudaStream_t st);
 
-// binning.cu (CUB): temp-storage sizing and the two sorts + scan
-size_t depth_sort_temp_bytes(int P);
-size_t tile_sort_temp_bytes(int64_t D, int tile_bits);
-int sort_by_depth_and_scan(const GeomBuf& g, int P, cudaStream_t st);
-int sort_by_tile(const BinBuf& b, int64_t D, int tile_bits, cudaStream_t st);
+// binning.cu (CUB): temp-storage sizing, scan and pair sort
+size_t scan_temp_bytes(int P);
+size_t pair_sort_temp_bytes(int64_t D, int key_bits);
+int scan_bin_counts(const GeomBuf& g, int P, cudaStream_t st);
+int sort_pairs(const BinBuf& b, int64_t D, int key_bits, cudaStream_t st);
 
 }  // namespace b200gs

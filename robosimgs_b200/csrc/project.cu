@@ -169,6 +169,18 @@ __device__ __forceinline__ TileRect reference_rect(float px, float py, int radiu
   return r;
 }
 
+// Binning granularity.  Pairs are sorted per *bin* of (16 << shift)^2 pixels; every 16x16 compositing
+// CTA walks the list of the bin it lies in and re-applies the reference rect (exactly) and the
+// ellipse test per record.  Coarser bins mean fewer (Gaussian, bin) pairs to emit and sort.
+__device__ __forceinline__ TileRect bin_rect(const TileRect& r, int shift) {
+  TileRect b;
+  b.x0 = r.x0 >> shift;
+  b.y0 = r.y0 >> shift;
+  b.x1 = (r.x1 > r.x0) ? ((r.x1 - 1) >> shift) + 1 : b.x0;
+  b.y1 = (r.y1 > r.y0) ? ((r.y1 - 1) >> shift) + 1 : b.y0;
+  return b;
+}
+
 // All span arithmetic uses explicitly rounded intrinsics / fixed PTX approximations, so the count
 // (k_project) and the emission (k_emit_*) see bit-identical spans wherever the code is inlined.
 __device__ __forceinline__ float sqrt_approx(float v) {
@@ -186,12 +198,15 @@ struct SpanCtx {
   float y_at_xext;  // dy at the right-most point of the ellipse
   float y_ext;
   float pad;
-  int ty0, ty1;     // tile rows the ellipse can reach, clipped to the reference rect
+  float bt, inv_bt; // bin edge in pixels and its reciprocal
+  int ty0, ty1;     // bin rows the ellipse can reach, clipped to the reference rect
 };
 
 __device__ __forceinline__ bool span_setup(SpanCtx& s, float x, float y, float A, float B, float C,
-                                           float thr, const TileRect& r) {
+                                           float thr, const TileRect& r, int bin_shift) {
   s.x = x; s.y = y; s.B = B;
+  s.bt = (float)(TILE << bin_shift);
+  s.inv_bt = 1.f / s.bt;   // power of two: exact
   const float tau = __fmul_rn(2.f, thr);
   s.det = __fmaf_rn(A, C, -__fmul_rn(B, B));
   s.ty0 = s.ty1 = 0;
@@ -204,20 +219,21 @@ __device__ __forceinline__ bool span_setup(SpanCtx& s, float x, float y, float A
   s.y_ext = __fmaf_rn(sqrt_approx(__fmul_rn(__fmul_rn(tau, A), inv_det)), 1.005f, 0.02f);
   s.y_at_xext = -__fmul_rn(__fmul_rn(B, s.x_ext), __frcp_rn(C));
   s.pad = __fmaf_rn(0.01f, s.x_ext, 0.02f);
-  // tile row ty holds pixel-centre rows [16 ty, 16 ty + 15]
-  const int lo = (int)ceilf(__fmul_rn(__fadd_rn(__fadd_rn(y, -s.y_ext), -(float)(TILE - 1)), 1.f / TILE));
-  const int hi = (int)floorf(__fmul_rn(__fadd_rn(y, s.y_ext), 1.f / TILE)) + 1;
+  // bin row ty holds pixel-centre rows [bt ty, bt ty + bt - 1]
+  const int lo = (int)ceilf(__fmul_rn(__fadd_rn(__fadd_rn(y, -s.y_ext), 1.f - s.bt), s.inv_bt));
+  const int hi = (int)floorf(__fmul_rn(__fadd_rn(y, s.y_ext), s.inv_bt)) + 1;
   s.ty0 = max(r.y0, lo);
   s.ty1 = min(r.y1, hi);
   return s.ty1 > s.ty0;
 }
 
-// tile-column span [c0,c1) of tile row ty: x-interval of the ellipse {A dx^2 + 2B dx dy + C dy^2 <=
-// tau} inside the band of pixel-centre rows [16 ty, 16 ty + 15], clipped to the reference rect.
+// bin-column span [c0,c1) of bin row ty: x-interval of the ellipse {A dx^2 + 2B dx dy + C dy^2 <=
+// tau} inside the band of pixel-centre rows [bt ty, bt ty + bt - 1], clipped to the reference rect.
 __device__ __forceinline__ void row_span(const SpanCtx& s, const TileRect& r, int ty, int& c0, int& c1) {
   c0 = c1 = 0;
-  float a = __fadd_rn((float)(ty * TILE) - 0.02f, -s.y);
-  float b = __fadd_rn((float)(ty * TILE + TILE - 1) + 0.02f, -s.y);
+  const float row0 = __fmul_rn((float)ty, s.bt);
+  float a = __fadd_rn(row0 - 0.02f, -s.y);
+  float b = __fadd_rn(row0 + (s.bt - 1.f) + 0.02f, -s.y);
   a = fmaxf(a, -s.y_ext);
   b = fminf(b, s.y_ext);
   if (a > b) return;
@@ -231,17 +247,17 @@ __device__ __forceinline__ void row_span(const SpanCtx& s, const TileRect& r, in
   if (-s.y_at_xext >= a && -s.y_at_xext <= b) xmin = -s.x_ext;  // left-most point inside the band
   const float X0 = __fadd_rn(s.x, __fadd_rn(xmin, -s.pad)), X1 = __fadd_rn(s.x, __fadd_rn(xmax, s.pad));
   // tile tx holds pixel centres [16 tx, 16 tx + 15]: intersects [X0,X1] iff 16tx <= X1 and 16tx+15 >= X0
-  int t0 = (int)ceilf(__fmul_rn(__fadd_rn(X0, -(float)(TILE - 1)), 1.f / TILE));
-  int t1 = (int)floorf(__fmul_rn(X1, 1.f / TILE)) + 1;
+  int t0 = (int)ceilf(__fmul_rn(__fadd_rn(X0, 1.f - s.bt), s.inv_bt));
+  int t1 = (int)floorf(__fmul_rn(X1, s.inv_bt)) + 1;
   t0 = max(t0, r.x0);
   t1 = min(t1, r.x1);
   if (t1 > t0) { c0 = t0; c1 = t1; }
 }
 
 __device__ __forceinline__ uint32_t count_tiles(float x, float y, float A, float B, float C, float thr,
-                                                const TileRect& r) {
+                                                const TileRect& r, int bin_shift) {
   SpanCtx s;
-  if (!span_setup(s, x, y, A, B, C, thr, r)) return 0;
+  if (!span_setup(s, x, y, A, B, C, thr, r, bin_shift)) return 0;
   uint32_t n = 0;
   for (int ty = s.ty0; ty < s.ty1; ty++) {
     int c0, c1;
@@ -261,7 +277,6 @@ __global__ void __launch_bounds__(256) k_project(ProjectArgs a) {
   CamConst c;
   load_cam(c, a.view, a.proj, a.campos);
 
-  a.idx[i] = (uint32_t)i;
   uint32_t key = 0xFFFFFFFFu, ntiles = 0;
   int radius = 0;
 
@@ -303,7 +318,7 @@ __global__ void __launch_bounds__(256) k_project(ProjectArgs a) {
         const float o = __ldg(a.opac + i);
         // 0.5*q <= thr  <=>  o*exp(-0.5 q) >= 1/255 ; slack keeps the test conservative
         const float thr = __logf(255.f * o) + 0.01f;
-        ntiles = (o > 0.f) ? count_tiles(px, py, A, B, C, thr, r) : 0u;
+        ntiles = (o > 0.f) ? count_tiles(px, py, A, B, C, thr, bin_rect(r, a.bin_shift), a.bin_shift) : 0u;
         if (ntiles > 0) {
           float rgb[3];
           uint32_t clampbits = 0;
@@ -335,7 +350,7 @@ __global__ void __launch_bounds__(256) k_project(ProjectArgs a) {
           float4* rec = a.rec + (size_t)i * REC_F4;
           rec[0] = make_float4(px, py, A, B);
           rec[1] = make_float4(C, o, thr, __uint_as_float((uint32_t)i));
-          rec[2] = make_float4(rgb[0], rgb[1], rgb[2], vz);
+          rec[2] = make_float4(rgb[0], rgb[1], rgb[2], (float)irad);
         }
       }
     }
@@ -346,27 +361,25 @@ __global__ void __launch_bounds__(256) k_project(ProjectArgs a) {
 }
 
 // ==================================================================================================
-// K3: emit (tile id, Gaussian id) pairs in depth order.  Thread r handles the r-th nearest Gaussian;
-// offsets[] is the inclusive scan of the per-Gaussian tile counts in that order, so the pair list is
-// depth-major and a stable sort on the tile id alone yields the (tile, depth) order of the public
-// algorithm's 64-bit key sort.
+// K3: emit ((bin << 32) | depth bits, Gaussian id) pairs in index order; offsets[] is the inclusive
+// scan of the per-Gaussian bin counts.
 // ==================================================================================================
 __global__ void __launch_bounds__(256) k_emit_pairs(EmitArgs a) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
   const uint32_t cap = a.capacity;
-  const bool valid = r < a.P;
-  uint32_t g = 0, n = 0, off = 0;
+  const uint32_t g = (uint32_t)r;
+  uint32_t n = 0, off = 0;
   float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
   int radius = 0;
-  if (valid) {
-    g = a.perm[r];
-    n = a.tiles[g];
+  uint64_t depth = 0;
+  if (r < a.P) {
+    n = a.tiles[r];
     if (n) {
       off = a.offsets[r] - n;
-      q0 = a.rec[(size_t)g * REC_F4];
-      q1 = a.rec[(size_t)g * REC_F4 + 1];
-      radius = a.radii[g];
+      q0 = a.rec[(size_t)r * REC_F4];
+      q1 = a.rec[(size_t)r * REC_F4 + 1];
+      radius = a.radii[r];
+      depth = a.depth_key[r];
     }
   }
   // ---- small footprints: one thread writes its own pairs ----
@@ -374,27 +387,27 @@ __global__ void __launch_bounds__(256) k_emit_pairs(EmitArgs a) {
   if (n > 0 && !big) {
     const uint32_t end = off + n;
     uint32_t o = off;
-    const TileRect rect = reference_rect(q0.x, q0.y, radius, a.gx, a.gy);
+    const TileRect rect = bin_rect(reference_rect(q0.x, q0.y, radius, a.gx, a.gy), a.bin_shift);
     SpanCtx s;
-    if (span_setup(s, q0.x, q0.y, q0.z, q0.w, q1.x, q1.z, rect)) {
+    if (span_setup(s, q0.x, q0.y, q0.z, q0.w, q1.x, q1.z, rect, a.bin_shift)) {
       for (int ty = s.ty0; ty < s.ty1; ty++) {
         int c0, c1;
         row_span(s, rect, ty, c0, c1);
         for (int tx = c0; tx < c1 && o < end; tx++, o++) {
           if (o < cap) {
-            a.keys[o] = (uint32_t)(ty * a.gx + tx);
+            a.keys[o] = ((uint64_t)(uint32_t)(ty * a.gbx + tx) << 32) | depth;
             a.vals[o] = g;
           }
         }
       }
     }
-    // defensive: never leave unwritten slots (count and emit share band_x_extent, so o == end)
+    // defensive: never leave unwritten slots (count and emit share row_span, so o == end)
     for (; o < end; o++) {
-      if (o < cap) { a.keys[o] = a.invalid_tile; a.vals[o] = g; }
+      if (o < cap) { a.keys[o] = (uint64_t)a.invalid_tile << 32; a.vals[o] = g; }
     }
   }
-  // ---- large footprints go to a global queue; k_emit_big spreads them over the whole GPU (they
-  // are depth-sorted, i.e. the nearest = largest splats would otherwise pile up in a few warps) ----
+  // ---- large footprints go to a global queue; k_emit_big emits them one warp per Gaussian so a
+  // few screen-filling splats cannot serialise a warp ----
   if (big) a.big_queue[atomicAdd(a.big_count, 1u)] = (uint32_t)r;
   // ---- speculative capacity: pad [D, capacity) with the invalid tile id so the sort can run on a
   // host-known item count while D is still on the device ----
@@ -402,7 +415,7 @@ __global__ void __launch_bounds__(256) k_emit_pairs(EmitArgs a) {
     const uint32_t D = a.P > 0 ? a.offsets[a.P - 1] : 0u;
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = D + (uint32_t)r; i < cap; i += stride) {
-      a.keys[i] = a.invalid_tile;
+      a.keys[i] = (uint64_t)a.invalid_tile << 32;
       a.vals[i] = 0u;
     }
   }
@@ -418,14 +431,14 @@ __global__ void __launch_bounds__(256) k_emit_big(EmitArgs a) {
   const uint32_t count = *a.big_count;
   const uint32_t cap = a.capacity;
   for (uint32_t w = warp_global; w < count; w += nwarps) {
-    const uint32_t r = a.big_queue[w];
-    const uint32_t g = a.perm[r];
+    const uint32_t g = a.big_queue[w];
     const uint32_t n = a.tiles[g];
-    const uint32_t off = a.offsets[r] - n, end = off + n;
+    const uint32_t off = a.offsets[g] - n, end = off + n;
+    const uint64_t depth = a.depth_key[g];
     const float4 q0 = a.rec[(size_t)g * REC_F4], q1 = a.rec[(size_t)g * REC_F4 + 1];
-    const TileRect rect = reference_rect(q0.x, q0.y, a.radii[g], a.gx, a.gy);
+    const TileRect rect = bin_rect(reference_rect(q0.x, q0.y, a.radii[g], a.gx, a.gy), a.bin_shift);
     SpanCtx s;
-    const bool ok = span_setup(s, q0.x, q0.y, q0.z, q0.w, q1.x, q1.z, rect);
+    const bool ok = span_setup(s, q0.x, q0.y, q0.z, q0.w, q1.x, q1.z, rect, a.bin_shift);
     uint32_t o = off;
     for (int y_base = s.ty0; ok && y_base < s.ty1; y_base += 32) {
       const int ty = y_base + lane;
@@ -445,11 +458,11 @@ __global__ void __launch_bounds__(256) k_emit_big(EmitArgs a) {
         if (l_i == 0) continue;
         const uint32_t o_i = __shfl_sync(0xffffffffu, row_off, i);
         const int c_i = __shfl_sync(0xffffffffu, c0, i);
-        const uint32_t tile0 = (uint32_t)((y_base + i) * a.gx + c_i);
+        const uint32_t tile0 = (uint32_t)((y_base + i) * a.gbx + c_i);
         for (uint32_t k = lane; k < l_i; k += 32) {
           const uint32_t idx = o_i + k;
           if (idx < end && idx < cap) {
-            a.keys[idx] = tile0 + k;
+            a.keys[idx] = ((uint64_t)(tile0 + k) << 32) | depth;
             a.vals[idx] = g;
           }
         }
@@ -457,7 +470,7 @@ __global__ void __launch_bounds__(256) k_emit_big(EmitArgs a) {
       o += __shfl_sync(0xffffffffu, incl, 31);
     }
     for (uint32_t idx = min(o, end) + lane; idx < end; idx += 32) {
-      if (idx < cap) { a.keys[idx] = a.invalid_tile; a.vals[idx] = g; }
+      if (idx < cap) { a.keys[idx] = (uint64_t)a.invalid_tile << 32; a.vals[idx] = g; }
     }
   }
 }
@@ -468,10 +481,10 @@ __global__ void __launch_bounds__(256) k_emit_big(EmitArgs a) {
 __global__ void __launch_bounds__(256) k_tile_ranges(RangesArgs a) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= a.D) return;
-  const uint32_t t = a.keys_sorted[j];
+  const uint32_t t = (uint32_t)(a.keys_sorted[j] >> 32);
   if (t >= a.num_tiles) return;   // padding of the speculative capacity
-  if (j == 0 || a.keys_sorted[j - 1] != t) a.ranges[t].x = (uint32_t)j;
-  if (j == a.D - 1 || a.keys_sorted[j + 1] != t) a.ranges[t].y = (uint32_t)(j + 1);
+  if (j == 0 || (uint32_t)(a.keys_sorted[j - 1] >> 32) != t) a.ranges[t].x = (uint32_t)j;
+  if (j == a.D - 1 || (uint32_t)(a.keys_sorted[j + 1] >> 32) != t) a.ranges[t].y = (uint32_t)(j + 1);
 }
 
 // ==================================================================================================

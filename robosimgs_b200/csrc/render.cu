@@ -50,6 +50,16 @@ __device__ __forceinline__ bool block_may_contribute(float x, float y, float A, 
   return 0.5f * q - 4e-6f * mag <= thr;
 }
 
+// Exactly the reference's tile rect (project.cu:reference_rect): is 16x16 tile (tx,ty) inside the
+// square [c - r, c + r] of a splat?  Needed when pairs are binned coarser than 16 px.
+__device__ __forceinline__ bool tile_in_reference_rect(float px, float py, float fr, int tx, int ty, int gx, int gy) {
+  const int x0 = min(gx, max(0, (int)((px - fr) / TILE)));
+  const int y0 = min(gy, max(0, (int)((py - fr) / TILE)));
+  const int x1 = min(gx, max(0, (int)((px + fr + (TILE - 1)) / TILE)));
+  const int y1 = min(gy, max(0, (int)((py + fr + (TILE - 1)) / TILE)));
+  return tx >= x0 && tx < x1 && ty >= y0 && ty < y1;
+}
+
 enum { GATHER_TMA = 0, GATHER_LDGSTS = 1 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -142,7 +152,8 @@ __global__ void __launch_bounds__(256) k_render_fwd(RenderArgs a) {
   __shared__ __align__(8) uint64_t full[STAGES];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint2 range = a.ranges[blockIdx.y * gridDim.x + blockIdx.x];
+  const uint2 range = a.ranges[(blockIdx.y >> a.bin_shift) * a.gbx + (blockIdx.x >> a.bin_shift)];
+  const bool coarse = a.bin_shift != 0;
   const uint32_t n = range.y - range.x;
   const uint32_t nchunks = (n + CH - 1) / CH;
   GatherRing<MODE> ring{sm, full, a.point_list + range.x, a.rec, n, nchunks, 0u, tid};
@@ -172,6 +183,8 @@ __global__ void __launch_bounds__(256) k_render_fwd(RenderArgs a) {
       if (j < cnt) {
         const float4 q0 = st[j * REC_F4], q1 = st[j * REC_F4 + 1];
         hit = block_may_contribute(q0.x, q0.y, q0.z, q0.w, q1.x, q1.z, rx0, ry0, rx1, ry1);
+        if (coarse && hit)
+          hit = tile_in_reference_rect(q0.x, q0.y, st[j * REC_F4 + 2].w, blockIdx.x, blockIdx.y, gridDim.x, gridDim.y);
       }
       uint32_t mask = __ballot_sync(0xffffffffu, hit);
       while (mask) {
@@ -259,7 +272,8 @@ __global__ void __launch_bounds__(256) k_render_bwd(RenderBwdArgs a) {
   __shared__ __align__(8) uint64_t full[STAGES];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint2 range = a.ranges[blockIdx.y * gridDim.x + blockIdx.x];
+  const uint2 range = a.ranges[(blockIdx.y >> a.bin_shift) * a.gbx + (blockIdx.x >> a.bin_shift)];
+  const bool coarse = a.bin_shift != 0;
   const uint32_t n = range.y - range.x;
   const uint32_t nchunks = (n + CH - 1) / CH;
   GatherRing<MODE> ring{sm, full, a.point_list + range.x, a.rec, n, nchunks, 0u, tid};
@@ -302,6 +316,8 @@ __global__ void __launch_bounds__(256) k_render_bwd(RenderBwdArgs a) {
       if (j < cnt) {
         const float4 q0 = st[j * REC_F4], q1 = st[j * REC_F4 + 1];
         hit = block_may_contribute(q0.x, q0.y, q0.z, q0.w, q1.x, q1.z, rx0, ry0, rx1, ry1);
+        if (coarse && hit)
+          hit = tile_in_reference_rect(q0.x, q0.y, st[j * REC_F4 + 2].w, blockIdx.x, blockIdx.y, gridDim.x, gridDim.y);
       }
       uint32_t mask = __ballot_sync(0xffffffffu, hit);
       while (mask) {

@@ -32,7 +32,7 @@ def test_buffer_sizes_are_host_only_and_monotone(built):
     L = _cabi.lib()
     g, b, i = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
     assert L.b200gs_buffer_sizes(1000, 1080, 1920, 50000, ctypes.byref(g), ctypes.byref(b), ctypes.byref(i)) == 0
-    assert g.value >= 1000 * (48 + 6 * 4 + 1) and b.value >= 50000 * 16 and i.value >= 1080 * 1920 * 20
+    assert g.value >= 1000 * (48 + 4 * 4 + 1) and b.value >= 50000 * 24 and i.value >= 1080 * 1920 * 20
     g2 = ctypes.c_size_t()
     L.b200gs_buffer_sizes(2000, 1080, 1920, 0, ctypes.byref(g2), None, None)
     assert g2.value > g.value
