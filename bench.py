@@ -63,7 +63,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
             return
@@ -172,7 +172,7 @@ def run_b200(args):
     import torch.distributed as dist
     import __graft_entry__ as ge
     ge.build()
-    from robosimgs_b200 import GaussianRasterizer, _cabi
+    from robosimgs_b200 import GaussianRasterizer, _cabi, export_rgb8
     from robosimgs_b200.rasterizer import GaussianRasterizationSettings
     from robosimgs_b200.scenes import mse_loss, room_scene, room_target, settings_from_camera
 
@@ -286,9 +286,9 @@ def run_b200(args):
     for c in cams:
         pack = torch.cat([c.viewmatrix.reshape(-1), c.projmatrix.reshape(-1), c.campos.reshape(-1)]).pin_memory()
         host_cams.append((c, pack))
-    host_frames = [torch.empty((3, H_IMG, W_IMG), dtype=torch.float32).pin_memory() for _ in range(2)]
+    host_frames = [torch.empty((H_IMG, W_IMG, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
     h2d_bytes = host_cams[0][1].numel() * 4
-    d2h_bytes = host_frames[0].numel() * 4
+    d2h_bytes = host_frames[0].numel()
     copy_stream = torch.cuda.Stream(device=dev)
     frame_done = [torch.cuda.Event(), torch.cuda.Event()]
 
@@ -298,6 +298,7 @@ def run_b200(args):
         rs = GaussianRasterizationSettings(c.image_height, c.image_width, c.tanfovx, c.tanfovy, bg, 1.0,
                                            d[0:16].view(4, 4), d[16:32].view(4, 4), SH_DEG, d[32:35], False, False)
         col, _ = render(rs)
+        col = export_rgb8(col)      # 8-bit HWC frame, the format the datagen sweep stores
         # device->host read of the finished frame on a side stream: overlaps the next frame's render
         ready = torch.cuda.Event()
         ready.record()
@@ -358,9 +359,9 @@ def run_b200(args):
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": "Mpixels/s", "ms_per_step": e2e_ms / K,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                "what": "GaussianRasterizer.forward per frame: camera (view, proj, campos) from pinned host memory, "
-                        "finished fp32 frame copied to pinned host memory (side stream, double-buffered); scene "
-                        "resident in HBM as in the reference's render loop"},
+                "what": "GaussianRasterizer.forward + export_rgb8 per frame: camera (view, proj, campos) from pinned "
+                        "host memory, finished 8-bit RGB frame copied to pinned host memory (side stream, "
+                        "double-buffered); scene resident in HBM as in the reference's render loop"},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": dom_gbs, "peak": peak, "unit": "GB/s",
                      "frac": dom_gbs / peak, "traffic": traffic, "peak_source": peak_src,

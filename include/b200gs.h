@@ -119,6 +119,13 @@ int b200gs_backward(const B200GSParams* prm, const float* bg, const float* viewm
 int b200gs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
                         const float* projmatrix, uint8_t* present, void* stream);
 
+/* Frame export for the datagen sweep: color[3][H][W] fp32 -> out_hwc[H][W][3] 8-bit RGB
+ * (clamp to [0,1], *255, round to nearest).  The reference's per-frame scene render feeds image
+ * datasets (/root/reference/README.md:85); exporting on the device cuts the device->host read of a
+ * finished 1080p frame from 24.9 MB to 6.2 MB. */
+int b200gs_export_rgb8(const float* color, int32_t image_height, int32_t image_width,
+                       uint8_t* out_hwc, void* stream);
+
 /* Sizes of the forward scratch buffers for given P, H, W (geom, img) and D (binning); lets a
  * caller pre-size arenas.  Any of the out pointers may be NULL. */
 int b200gs_buffer_sizes(int32_t P, int32_t image_height, int32_t image_width, int64_t D,

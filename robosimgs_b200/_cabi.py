@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libb200gs.so")
 EXPORTED_SYMBOLS = (
     "b200gs_forward", "b200gs_backward", "b200gs_mark_visible", "b200gs_buffer_sizes",
     "b200gs_last_error", "b200gs_version", "b200gs_launch_count",
-    "b200gs_profile_enable", "b200gs_profile_read", "b200gs_stage_name",
+    "b200gs_profile_enable", "b200gs_profile_read", "b200gs_stage_name", "b200gs_export_rgb8",
 )
 NUM_STAGES = 8
 
@@ -71,6 +71,8 @@ def lib():
     L.b200gs_version.restype = C.c_int
     L.b200gs_launch_count.restype = C.c_int64
     L.b200gs_launch_count.argtypes = [C.c_int]
+    L.b200gs_export_rgb8.restype = C.c_int
+    L.b200gs_export_rgb8.argtypes = [fp, C.c_int32, C.c_int32, vp, vp]
     L.b200gs_profile_enable.argtypes = [C.c_int]
     L.b200gs_profile_read.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int]
     L.b200gs_stage_name.restype = C.c_char_p

@@ -438,6 +438,21 @@ int b200gs_backward(const B200GSParams* prm, const float* bg, const float* viewm
   return debug_sync(prm, st, "project backward");
 }
 
+int b200gs_export_rgb8(const float* color, int32_t H, int32_t W, uint8_t* out_hwc, void* stream) {
+  g_err[0] = 0;
+  if (!color || !out_hwc || H <= 0 || W <= 0) {
+    set_error("export_rgb8: invalid arguments");
+    return B200GS_ERR_INVALID_ARG;
+  }
+  if ((reinterpret_cast<uintptr_t>(color) & 15) || (reinterpret_cast<uintptr_t>(out_hwc) & 3)) {
+    set_error("export_rgb8: color must be 16-byte aligned, out 4-byte aligned");
+    return B200GS_ERR_INVALID_ARG;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  launch_export_rgb8(color, H, W, out_hwc, st);
+  return check_cuda(cudaGetLastError(), "export_rgb8");
+}
+
 int b200gs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
                         const float* projmatrix, uint8_t* present, void* stream) {
   g_err[0] = 0;

@@ -79,6 +79,7 @@ void launch_mark_visible(int P, const float* means, const float* view, uint8_t* 
 void launch_project_bwd(const ProjectBwdArgs& a, int deg, cudaStream_t st);
 void launch_render(const RenderArgs& a, cudaStream_t st);
 void launch_render_bwd(const RenderBwdArgs& a, cudaStream_t st);
+void launch_export_rgb8(const float* color, int H, int W, uint8_t* out, cudaStream_t st);
 
 // binning.cu (CUB): temp-storage sizing, scan and pair sort
 size_t scan_temp_bytes(int P);

@@ -377,6 +377,39 @@ __global__ void __launch_bounds__(256) k_render_bwd(RenderBwdArgs a) {
   if (MODE == GATHER_LDGSTS) cp_async_wait<0>();
 }
 
+// Frame export for the datagen sweep: CHW fp32 colour -> HWC 8-bit RGB (clamp to [0,1], round to
+// nearest), 4 pixels per thread so every thread writes three aligned 32-bit words.
+__global__ void __launch_bounds__(256) k_export_rgb8(const float* __restrict__ color, int H, int W,
+                                                     uint8_t* __restrict__ out) {
+  const size_t npx = (size_t)H * W;
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // group of 4 pixels
+  const size_t p0 = q * 4;
+  if (p0 >= npx) return;
+  auto cvt = [](float v) { return (uint32_t)__float2int_rn(__saturatef(v) * 255.f); };
+  if (p0 + 3 < npx && (npx & 3) == 0) {
+    const float4 r = *reinterpret_cast<const float4*>(color + p0);
+    const float4 g = *reinterpret_cast<const float4*>(color + npx + p0);
+    const float4 b = *reinterpret_cast<const float4*>(color + 2 * npx + p0);
+    const uint32_t w0 = cvt(r.x) | (cvt(g.x) << 8) | (cvt(b.x) << 16) | (cvt(r.y) << 24);
+    const uint32_t w1 = cvt(g.y) | (cvt(b.y) << 8) | (cvt(r.z) << 16) | (cvt(g.z) << 24);
+    const uint32_t w2 = cvt(b.z) | (cvt(r.w) << 8) | (cvt(g.w) << 16) | (cvt(b.w) << 24);
+    uint32_t* o = reinterpret_cast<uint32_t*>(out + p0 * 3);
+    o[0] = w0; o[1] = w1; o[2] = w2;
+  } else {
+    for (size_t p = p0; p < npx && p < p0 + 4; p++) {
+      out[p * 3 + 0] = (uint8_t)cvt(color[p]);
+      out[p * 3 + 1] = (uint8_t)cvt(color[npx + p]);
+      out[p * 3 + 2] = (uint8_t)cvt(color[2 * npx + p]);
+    }
+  }
+}
+
+void launch_export_rgb8(const float* color, int H, int W, uint8_t* out, cudaStream_t st) {
+  const size_t groups = ((size_t)H * W + 3) / 4;
+  k_export_rgb8<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(color, H, W, out);
+  count_launch();
+}
+
 static int gather_mode() {
   static const int mode = [] {
     const char* e = getenv("B200GS_GATHER");

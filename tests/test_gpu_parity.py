@@ -219,3 +219,14 @@ def test_speculative_pair_capacity_paths_are_bit_identical():
         assert torch.isfinite(args[0].grad).all()
     assert outs[0][1] == outs[1][1] == outs[2][1] > 17
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][0], outs[2][0])
+
+
+def test_export_rgb8_matches_numpy():
+    from robosimgs_b200 import export_rgb8
+    g = torch.Generator().manual_seed(5)
+    for H, W in ((48, 64), (23, 37)):
+        col = (torch.rand(3, H, W, generator=g) * 1.4 - 0.2).cuda()
+        out = export_rgb8(col).cpu().numpy()
+        ref = np.rint(np.clip(col.cpu().numpy(), 0, 1) * 255.0).astype(np.uint8).transpose(1, 2, 0)
+        assert out.shape == (H, W, 3) and np.abs(out.astype(int) - ref.astype(int)).max() <= 1
+        assert (out != ref).mean() < 1e-3       # only exact .5 ties may differ
