@@ -254,6 +254,10 @@ def run_b200(args):
     with torch.no_grad():
         fwd_ms = timed(lambda s: render(settings_dev[Wm + s]), K)
     launches = _cabi.launch_count(reset=True)
+    if world > 1:
+        lt = torch.tensor([launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
     stages_fwd = _cabi.profile_read(reset=True)
     _cabi.profile_enable(False)
 
