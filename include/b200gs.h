@@ -126,6 +126,34 @@ int b200gs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix
 int b200gs_export_rgb8(const float* color, int32_t image_height, int32_t image_width,
                        uint8_t* out_hwc, void* stream);
 
+/*
+ * Data formats either side of the rasterizer.
+ *
+ * b200gs_ply_activate: vertex records of a 3DGS .ply (the hand-off format the reference names,
+ * /root/reference/README.md:75; binary little-endian float properties x,y,z,nx,ny,nz,f_dc_0..2,
+ * f_rest_0..3*n_rest-1,opacity,scale_0..2,rot_0..3, stored PRE-activation) -> the packed tensors
+ * b200gs_forward takes: sigmoid(opacity), exp(scale), normalised quaternion, shs[P][1+n_rest][3]
+ * (f_rest is channel-major in the file).  `vertices` is the device copy of the vertex block; the
+ * layout gives the record stride and property offsets in floats.
+ */
+typedef struct B200GSPlyLayout {
+  int32_t stride;      /* floats per vertex record */
+  int32_t off_xyz, off_fdc, off_frest, n_rest, off_opacity, off_scale, off_rot;
+} B200GSPlyLayout;
+int b200gs_ply_activate(int32_t P, const float* vertices, const B200GSPlyLayout* layout, float* means3D,
+                        float* shs, float* opacities, float* scales, float* rotations, void* stream);
+
+/*
+ * b200gs_transform_gaussians: per-link rigid pose update of object Gaussians for the articulated
+ * composite (links / hinge as produced by /root/reference/Articulation/urdf_generation/pipeline.py:
+ * 290-357): means_out = R_l * mean + t_l, rots_out = q_l (x) rot, l = link_ids[i] (NULL = link 0).
+ * link_transforms[L][12] are row-major 3x4, link_quats[L][4] are (w,x,y,z); in/out may alias.
+ */
+int b200gs_transform_gaussians(int32_t n, const float* means_in, const float* rots_in,
+                               const int32_t* link_ids, const float* link_transforms,
+                               const float* link_quats, int32_t L, float* means_out, float* rots_out,
+                               void* stream);
+
 /* Sizes of the forward scratch buffers for given P, H, W (geom, img) and D (binning); lets a
  * caller pre-size arenas.  Any of the out pointers may be NULL. */
 int b200gs_buffer_sizes(int32_t P, int32_t image_height, int32_t image_width, int64_t D,
@@ -139,6 +167,14 @@ int b200gs_version(void);
 
 /* Kernel launches issued by this process since the last call with reset != 0 (bench accounting). */
 int64_t b200gs_launch_count(int reset);
+
+/*
+ * Process-wide tuning knobs (never change results):
+ *   "bin_shift": -1 automatic (default), 0..5 = sort pairs per (16 << shift)^2 pixel bins
+ *   "gather":     1 LDGSTS record gather in the compositing kernels (default), 0 TMA bulk copies
+ * Environment equivalents read at first use: B200GS_BIN_SHIFT, B200GS_GATHER=tma|ldgsts.
+ */
+int b200gs_set_option(const char* name, int value);
 
 /*
  * Optional per-stage device timing (used by bench.py for the roofline figures).  While enabled,

@@ -15,6 +15,7 @@ EXPORTED_SYMBOLS = (
     "b200gs_forward", "b200gs_backward", "b200gs_mark_visible", "b200gs_buffer_sizes",
     "b200gs_last_error", "b200gs_version", "b200gs_launch_count",
     "b200gs_profile_enable", "b200gs_profile_read", "b200gs_stage_name", "b200gs_export_rgb8",
+    "b200gs_set_option", "b200gs_ply_activate", "b200gs_transform_gaussians",
 )
 NUM_STAGES = 8
 
@@ -26,6 +27,11 @@ class B200GSParams(C.Structure):
         ("tanfovx", C.c_float), ("tanfovy", C.c_float), ("scale_modifier", C.c_float),
         ("prefiltered", C.c_int32), ("debug", C.c_int32), ("pair_capacity_hint", C.c_int64),
     ]
+
+
+class B200GSPlyLayout(C.Structure):
+    _fields_ = [("stride", C.c_int32), ("off_xyz", C.c_int32), ("off_fdc", C.c_int32), ("off_frest", C.c_int32),
+                ("n_rest", C.c_int32), ("off_opacity", C.c_int32), ("off_scale", C.c_int32), ("off_rot", C.c_int32)]
 
 
 RESIZE_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
@@ -73,6 +79,12 @@ def lib():
     L.b200gs_launch_count.argtypes = [C.c_int]
     L.b200gs_export_rgb8.restype = C.c_int
     L.b200gs_export_rgb8.argtypes = [fp, C.c_int32, C.c_int32, vp, vp]
+    L.b200gs_ply_activate.restype = C.c_int
+    L.b200gs_ply_activate.argtypes = [C.c_int32, fp, C.POINTER(B200GSPlyLayout), fp, fp, fp, fp, fp, vp]
+    L.b200gs_transform_gaussians.restype = C.c_int
+    L.b200gs_transform_gaussians.argtypes = [C.c_int32, fp, fp, vp, fp, fp, C.c_int32, fp, fp, vp]
+    L.b200gs_set_option.restype = C.c_int
+    L.b200gs_set_option.argtypes = [C.c_char_p, C.c_int]
     L.b200gs_profile_enable.argtypes = [C.c_int]
     L.b200gs_profile_read.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int]
     L.b200gs_stage_name.restype = C.c_char_p
@@ -101,3 +113,8 @@ def profile_read(reset: bool = True) -> dict:
     calls = (C.c_int32 * NUM_STAGES)()
     check(L.b200gs_profile_read(ms, calls, 1 if reset else 0))
     return {L.b200gs_stage_name(i).decode(): (float(ms[i]), int(calls[i])) for i in range(NUM_STAGES)}
+
+
+def set_option(name: str, value: int) -> None:
+    """Tuning knobs of the library ("bin_shift": -1 auto / 0..5, "gather": 0 TMA / 1 LDGSTS)."""
+    check(lib().b200gs_set_option(name.encode(), int(value)))

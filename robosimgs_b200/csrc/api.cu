@@ -68,13 +68,16 @@ struct StageTimer {
 // log2(bin edge / 16): pairs are binned per (16 << shift)^2 pixels (see project.cu:bin_rect).
 // Default: the smallest shift that leaves at most 255 bins (bin id fits 8 key bits -> 40-bit sort
 // keys), capped at 3 (64 compositing CTAs share one bin list).  B200GS_BIN_SHIFT overrides.
+static std::atomic<int> g_bin_shift_override{-2};   // -2: not initialised, -1: automatic
+
 static int bin_shift_for(int gx, int gy) {
-  static const int forced = [] {
+  int forced = g_bin_shift_override.load();
+  if (forced == -2) {
     const char* e = getenv("B200GS_BIN_SHIFT");
-    if (!e) return -1;
-    const int s = atoi(e);
-    return s < 0 ? 0 : (s > 5 ? 5 : s);
-  }();
+    forced = e ? atoi(e) : -1;
+    forced = forced < -1 ? -1 : (forced > 5 ? 5 : forced);
+    g_bin_shift_override.store(forced);
+  }
   if (forced >= 0) return forced;
   int s = 0;
   while (s < 3 && (((gx + (1 << s) - 1) >> s) * ((gy + (1 << s) - 1) >> s)) > 255) s++;
@@ -198,6 +201,20 @@ const char* b200gs_last_error(void) { return g_err; }
 int b200gs_version(void) { return B200GS_VERSION; }
 int64_t b200gs_launch_count(int reset) {
   return reset ? g_launches.exchange(0) : g_launches.load();
+}
+
+int b200gs_set_option(const char* name, int value) {
+  g_err[0] = 0;
+  if (name && !strcmp(name, "bin_shift")) {
+    g_bin_shift_override.store(value < 0 ? -1 : (value > 5 ? 5 : value));
+    return 0;
+  }
+  if (name && !strcmp(name, "gather")) {
+    set_gather_mode(value);
+    return 0;
+  }
+  set_error("unknown option '%s'", name ? name : "(null)");
+  return B200GS_ERR_INVALID_ARG;
 }
 
 int b200gs_profile_enable(int on) {
@@ -451,6 +468,40 @@ int b200gs_export_rgb8(const float* color, int32_t H, int32_t W, uint8_t* out_hw
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   launch_export_rgb8(color, H, W, out_hwc, st);
   return check_cuda(cudaGetLastError(), "export_rgb8");
+}
+
+int b200gs_ply_activate(int32_t P, const float* vertices, const B200GSPlyLayout* layout, float* means3D,
+                        float* shs, float* opacities, float* scales, float* rotations, void* stream) {
+  g_err[0] = 0;
+  if (P < 0 || !layout || (P > 0 && (!vertices || !means3D || !shs || !opacities || !scales || !rotations))) {
+    set_error("ply_activate: invalid arguments");
+    return B200GS_ERR_INVALID_ARG;
+  }
+  const B200GSPlyLayout& L = *layout;
+  const int need = 3 + 3 + 3 * L.n_rest + 1 + 3 + 4;
+  if (L.stride < need || L.n_rest < 0 || L.off_xyz < 0 || L.off_fdc < 0 || L.off_frest < 0 || L.off_opacity < 0 ||
+      L.off_scale < 0 || L.off_rot < 0 || L.off_rot + 4 > L.stride || L.off_frest + 3 * L.n_rest > L.stride) {
+    set_error("ply_activate: inconsistent layout (stride %d)", L.stride);
+    return B200GS_ERR_INVALID_ARG;
+  }
+  int rc = launch_ply_activate(P, vertices, L, means3D, shs, opacities, scales, rotations,
+                               static_cast<cudaStream_t>(stream));
+  if (rc) return rc;
+  return check_cuda(cudaGetLastError(), "ply_activate");
+}
+
+int b200gs_transform_gaussians(int32_t n, const float* means_in, const float* rots_in,
+                               const int32_t* link_ids, const float* link_transforms,
+                               const float* link_quats, int32_t L, float* means_out, float* rots_out,
+                               void* stream) {
+  g_err[0] = 0;
+  if (n < 0 || L <= 0 || (n > 0 && (!means_in || !rots_in || !link_transforms || !link_quats || !means_out || !rots_out))) {
+    set_error("transform_gaussians: invalid arguments");
+    return B200GS_ERR_INVALID_ARG;
+  }
+  launch_transform_gaussians(n, means_in, rots_in, link_ids, link_transforms, link_quats, L, means_out, rots_out,
+                             static_cast<cudaStream_t>(stream));
+  return check_cuda(cudaGetLastError(), "transform_gaussians");
 }
 
 int b200gs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,

@@ -79,7 +79,15 @@ void launch_mark_visible(int P, const float* means, const float* view, uint8_t* 
 void launch_project_bwd(const ProjectBwdArgs& a, int deg, cudaStream_t st);
 void launch_render(const RenderArgs& a, cudaStream_t st);
 void launch_render_bwd(const RenderBwdArgs& a, cudaStream_t st);
+void set_gather_mode(int mode);  // 0: TMA bulk copy per record, 1: LDGSTS
 void launch_export_rgb8(const float* color, int H, int W, uint8_t* out, cudaStream_t st);
+
+// scene.cu
+int launch_ply_activate(int P, const float* v, const B200GSPlyLayout& L, float* means, float* shs, float* opac,
+                        float* scales, float* rots, cudaStream_t st);
+void launch_transform_gaussians(int n, const float* means_in, const float* rots_in, const int32_t* link_ids,
+                                const float* T, const float* Q, int L, float* means_out, float* rots_out,
+                                cudaStream_t st);
 
 // binning.cu (CUB): temp-storage sizing, scan and pair sort
 size_t scan_temp_bytes(int P);

@@ -20,6 +20,7 @@
 //  * adjoint: gradients of a record are reduced over the warp with a transposing butterfly
 //    (14 shuffles for 9 values) and leave the SM as one 9-lane RED.ADD.F32 to a 48-byte aligned
 //    accumulator row per Gaussian.
+#include <atomic>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -410,12 +411,18 @@ void launch_export_rgb8(const float* color, int H, int W, uint8_t* out, cudaStre
   count_launch();
 }
 
+static std::atomic<int> g_gather_mode{-1};
+
+void set_gather_mode(int mode) { g_gather_mode.store(mode == GATHER_TMA ? (int)GATHER_TMA : (int)GATHER_LDGSTS); }
+
 static int gather_mode() {
-  static const int mode = [] {
+  int m = g_gather_mode.load();
+  if (m < 0) {
     const char* e = getenv("B200GS_GATHER");
-    return (e && e[0] == 't') ? (int)GATHER_TMA : (int)GATHER_LDGSTS;
-  }();
-  return mode;
+    m = (e && e[0] == 't') ? (int)GATHER_TMA : (int)GATHER_LDGSTS;
+    g_gather_mode.store(m);
+  }
+  return m;
 }
 
 void launch_render(const RenderArgs& a, cudaStream_t st) {

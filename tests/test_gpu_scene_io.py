@@ -1,0 +1,93 @@
+"""GPU tests of the data-format kernels either side of the rasterizer: .ply
+activation/repack and the articulated pose update, each against a numpy statement of the same
+arithmetic, then end to end through the rasterizer against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import psnr, small_scene
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu(built):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def test_ply_activation_kernel_matches_numpy(tmp_path):
+    from robosimgs_b200 import ply
+    from robosimgs_b200.scenes import cube_scene
+    for degree, P in ((3, 1000), (0, 333), (1, 129)):
+        sc, _ = cube_scene(P=P, seed=11, degree=degree)
+        sc.rotations.mul_(torch.rand(P, 1, generator=torch.Generator().manual_seed(1)) + 0.5)   # un-normalised
+        path = str(tmp_path / f"s{degree}.ply")
+        ply.write_gaussian_ply(path, sc.means3D, sc.shs, sc.opacities, sc.scales, sc.rotations)
+        v, lay = ply.read_gaussian_ply(path)
+        got = ply.load_gaussian_ply(path, "cuda:0")
+        v64 = v.astype(np.float64)
+        M = 1 + lay["n_rest"]
+        assert got.sh_degree == degree and got.shs.shape == (P, M, 3)
+        assert np.array_equal(got.means3D.cpu().numpy(), v[:, 0:3])
+        shs = np.concatenate([v[:, lay["off_fdc"]:lay["off_fdc"] + 3][:, None, :],
+                              v[:, lay["off_frest"]:lay["off_frest"] + 3 * lay["n_rest"]].reshape(P, 3, lay["n_rest"]).transpose(0, 2, 1)], 1)
+        assert np.array_equal(got.shs.cpu().numpy(), shs)
+        assert np.allclose(got.opacities.cpu().numpy()[:, 0], 1 / (1 + np.exp(-v64[:, lay["off_opacity"]])), rtol=2e-6)
+        assert np.allclose(got.scales.cpu().numpy(), np.exp(v64[:, lay["off_scale"]:lay["off_scale"] + 3]), rtol=2e-6)
+        q = v64[:, lay["off_rot"]:lay["off_rot"] + 4]
+        assert np.allclose(got.rotations.cpu().numpy(), q / np.linalg.norm(q, axis=1, keepdims=True), atol=1e-6)
+
+
+def test_config2_through_ply_matches_oracle(tmp_path):
+    """BASELINE config 2 data path, reduced: tabletop scene -> .ply -> fused activation kernel ->
+    render of a reference view, against the oracle on the original tensors."""
+    from oracle import gs_oracle
+    from robosimgs_b200 import GaussianRasterizer, ply
+    from robosimgs_b200.scenes import settings_from_camera, tabletop_scene
+    sc, cams = tabletop_scene(P=20_000, resolution=320)
+    path = str(tmp_path / "tabletop.ply")
+    ply.write_gaussian_ply(path, sc.means3D, sc.shs, sc.opacities, sc.scales, sc.rotations)
+    g = ply.load_gaussian_ply(path, "cuda:0")
+    cam = cams["front"]
+    rs = settings_from_camera(cam, 3, device="cuda:0")
+    with torch.no_grad():
+        color, _ = GaussianRasterizer(rs)(g.means3D, torch.zeros_like(g.means3D), g.opacities, shs=g.shs,
+                                          scales=g.scales, rotations=g.rotations)
+    st = gs_oracle.forward(settings_from_camera(cam, 3), sc.means3D, sc.opacities, shs=sc.shs, scales=sc.scales,
+                           rotations=sc.rotations, dtype=np.float64)
+    assert psnr(color.cpu().numpy(), st.color) >= 60.0
+
+
+def test_transform_kernel_and_articulated_composite_match_oracle():
+    """BASELINE config 5, reduced: background + box-with-lid object, lid posed about the reference
+    hinge axis; pose kernel vs numpy, composite frame vs the oracle on numpy-posed parameters."""
+    from oracle import gs_oracle
+    from robosimgs_b200 import compositor as cp
+    from robosimgs_b200.scenes import Scene, settings_from_camera
+    bg, cam, rs = small_scene(P=1500, degree=1, W=200, H=152)
+    obj, link_ids, hinge = cp.box_with_lid_gaussians(900, 500, seed=5)
+    art = cp.ArticulatedScene(bg, obj, link_ids, "cuda:0")
+    base_q = cp.axis_angle_quat((1, 0.3, 0), 0.7)
+    scale, base_t = 1.5, (-0.2, -0.3, 0.4)
+    for theta in (0.0, cp.lid_angle(37)):
+        T0, q0 = cp.revolute_link_pose(cp.OPENBOX_HINGE_AXIS, hinge, 0.0, base_q=base_q, base_t=base_t, scale=scale)
+        T1, q1 = cp.revolute_link_pose((1, 0, 0), hinge, theta, base_q=base_q, base_t=base_t, scale=scale)
+        art.set_link_poses(np.stack([T0, T1]), np.stack([q0, q1]), scale=scale)
+        # numpy statement of the same pose update
+        T = np.stack([T0, T1])[link_ids.numpy()]
+        Q = np.stack([q0, q1])[link_ids.numpy()]
+        m = np.einsum("nij,nj->ni", T[:, :, :3], obj.means3D.numpy().astype(np.float64)) + T[:, :, 3]
+        r = np.stack([cp.quat_mul(Q[i], obj.rotations.numpy()[i].astype(np.float64)) for i in range(obj.P)])
+        assert np.allclose(art.means3D[art.P_bg:].cpu().numpy(), m, atol=2e-6)
+        assert np.allclose(art.rotations[art.P_bg:].cpu().numpy(), r, atol=2e-6)
+        assert torch.equal(art.means3D[:art.P_bg].cpu(), bg.means3D)            # background untouched
+        color, radii = art.render(settings_from_camera(cam, 1, bg=(0.2, 0.1, 0.4), device="cuda:0"))
+        obj_sh = np.zeros((obj.P, 4, 3), np.float32); obj_sh[:, :1] = obj.shs.numpy()
+        st = gs_oracle.forward(rs, np.concatenate([bg.means3D.numpy(), m]),
+                               np.concatenate([bg.opacities.numpy(), obj.opacities.numpy()]),
+                               shs=np.concatenate([bg.shs.numpy(), obj_sh]),
+                               scales=np.concatenate([bg.scales.numpy(), obj.scales.numpy() * scale]),
+                               rotations=np.concatenate([bg.rotations.numpy(), r]), dtype=np.float64)
+        assert psnr(color.cpu().numpy(), st.color) >= 60.0
+        assert (radii[art.P_bg:] > 0).sum() > 100        # the object is in view
