@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200gs.so")
+LIB_PATH = os.environ.get("B200GS_LIB_PATH") or os.path.join(_HERE, "lib", "libb200gs.so")  # env: A/B builds
 
 EXPORTED_SYMBOLS = (
     "b200gs_forward", "b200gs_backward", "b200gs_mark_visible", "b200gs_buffer_sizes",

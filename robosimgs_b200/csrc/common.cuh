@@ -64,6 +64,19 @@ struct ImgBuf {
 
 // ---- small math helpers ---------------------------------------------------------------------
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(hi, fmaxf(lo, v)); }
+// exp(x) for x <= 0 as one FMUL + one MUFU.EX2 (2 ulp; results below 2^-126 flush to 0, far below
+// the 1/255 alpha threshold they are compared against)
+__device__ __forceinline__ float exp_fast(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+  return r;
+}
+// 1/x for normal x as one MUFU.RCP (1 ulp)
+__device__ __forceinline__ float rcp_fast(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 
 // ---- mbarrier / TMA (1-D bulk copy) PTX wrappers ---------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -10,6 +10,13 @@
 
 namespace b200gs {
 
+#ifndef PROJECT_MIN_BLOCKS
+#define PROJECT_MIN_BLOCKS 4
+#endif
+#ifndef PROJECT_BWD_MIN_BLOCKS
+#define PROJECT_BWD_MIN_BLOCKS 3
+#endif
+
 struct CamConst {
   float v[16];
   float p[16];
@@ -271,7 +278,7 @@ __device__ __forceinline__ uint32_t count_tiles(float x, float y, float A, float
 // K1: projection + SH colour.  One thread per Gaussian.  DEG = -1: colours are precomputed.
 // ==================================================================================================
 template <int DEG>
-__global__ void __launch_bounds__(256) k_project(ProjectArgs a) {
+__global__ void __launch_bounds__(256, PROJECT_MIN_BLOCKS) k_project(ProjectArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.P) return;
   CamConst c;
@@ -508,7 +515,7 @@ __global__ void k_mark_visible(int P, const float* __restrict__ means, const flo
 // Every output element is written.
 // ==================================================================================================
 template <int DEG>
-__global__ void __launch_bounds__(256) k_project_bwd(ProjectBwdArgs a) {
+__global__ void __launch_bounds__(256, PROJECT_BWD_MIN_BLOCKS) k_project_bwd(ProjectBwdArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.P) return;
   constexpr int NB = (DEG < 0 ? 0 : (DEG + 1) * (DEG + 1));

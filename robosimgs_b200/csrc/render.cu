@@ -40,10 +40,10 @@ __device__ __forceinline__ bool block_may_contribute(float x, float y, float A, 
   const float cx = clampf(x, x0, x1), cy = clampf(y, y0, y1);
   const float dxe = cx - x, dye = cy - y;
   // vertical edge X = cx: minimise over Y
-  float dy1 = clampf(y - __fdividef(B * dxe, C), y0, y1) - y;
+  float dy1 = clampf(y - B * dxe * rcp_fast(C), y0, y1) - y;
   const float q1 = A * dxe * dxe + 2.f * B * dxe * dy1 + C * dy1 * dy1;
   // horizontal edge Y = cy: minimise over X
-  float dx2 = clampf(x - __fdividef(B * dye, A), x0, x1) - x;
+  float dx2 = clampf(x - B * dye * rcp_fast(A), x0, x1) - x;
   const float q2 = A * dx2 * dx2 + 2.f * B * dx2 * dye + C * dye * dye;
   const float q = fminf(q1, q2);
   // rounding guard: relative to the magnitude of the cancelling terms
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(256) k_render_fwd(RenderArgs a) {
         const float4 q0 = st[jj * REC_F4], q1 = st[jj * REC_F4 + 1], q2 = st[jj * REC_F4 + 2];
         const float dx = q0.x - pxf, dy = q0.y - pyf;
         const float power = -0.5f * (q0.z * dx * dx + q1.x * dy * dy) - q0.w * dx * dy;
-        const float alpha = fminf(0.99f, q1.y * __expf(power));
+        const float alpha = fminf(0.99f, q1.y * exp_fast(power));
         if (!done && power <= 0.f && alpha >= (1.f / 255.f)) {
           const float test_T = T * (1.f - alpha);
           if (test_T < 0.0001f) {
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(256) k_render_bwd(RenderBwdArgs a) {
         const float4 q0 = st[jj * REC_F4], q1 = st[jj * REC_F4 + 1], q2 = st[jj * REC_F4 + 2];
         const float dx = q0.x - pxf, dy = q0.y - pyf;
         const float power = -0.5f * (q0.z * dx * dx + q1.x * dy * dy) - q0.w * dx * dy;
-        const float G = __expf(power);
+        const float G = exp_fast(power);
         const float alpha = fminf(0.99f, q1.y * G);
         const bool valid = (c * CH + jj < ncontrib) && power <= 0.f && alpha >= (1.f / 255.f);
         if (!__any_sync(0xffffffffu, valid)) continue;
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(256) k_render_bwd(RenderBwdArgs a) {
           Cr = __fmaf_rn(q2.x, w, Cr);
           Cg = __fmaf_rn(q2.y, w, Cg);
           Cb = __fmaf_rn(q2.z, w, Cb);
-          const float inv1ma = __fdividef(1.f, 1.f - alpha);
+          const float inv1ma = rcp_fast(1.f - alpha);
           const float behind = (fin.x - Cr) * gr + (fin.y - Cg) * gg + (fin.z - Cb) * gb;
           const float dL_dalpha = T * (q2.x * gr + q2.y * gg + q2.z * gb) - inv1ma * (behind + bgterm);
           T = T * (1.f - alpha);
