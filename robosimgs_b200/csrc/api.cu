@@ -84,6 +84,24 @@ static int bin_shift_for(int gx, int gy) {
   return s;
 }
 
+// pair sort implementation.  Measured on B200 (tools/sort_ab.py): the single-launch cooperative
+// sort wins on small pair lists (C1, 17 k pairs: 60 vs 76 us) where CUB's six dependent launches
+// dominate, and loses above a few hundred thousand pairs (C3, 0.77 M: 127 vs 111 us; its five grid
+// barriers cost ~5 us each).  Mode 0 = CUB, 1 = automatic by size (default), 2 = cooperative
+// whenever it applies.
+static std::atomic<int> g_sort_mode{-1};
+constexpr int64_t COOP_SORT_AUTO_MAX = 256 * 1024;
+static bool use_coop_sort(int64_t n) {
+  int m = g_sort_mode.load();
+  if (m < 0) {
+    const char* e = getenv("B200GS_SORT");
+    m = !e ? 1 : (!strcmp(e, "cub") ? 0 : (!strcmp(e, "coop") ? 2 : 1));
+    g_sort_mode.store(m);
+  }
+  if (n <= 0 || m == 0) return false;
+  return n <= (m == 2 ? COOP_SORT_MAX_ITEMS : COOP_SORT_AUTO_MAX);
+}
+
 static int tile_bits_for(int num_tiles) {
   int bits = 1;
   while ((1 << bits) <= num_tiles) bits++;  // room for the invalid id == num_tiles
@@ -113,6 +131,7 @@ static BinBuf carve_binning(char* base, int64_t D, int tile_bits, size_t* bytes)
   b.keys_sorted = c.take<uint64_t>(D);
   b.keys = c.take<uint64_t>(D);
   b.vals = c.take<uint32_t>(D);
+  b.coop_hist = c.take<uint32_t>(coop_sort_hist_bytes() / sizeof(uint32_t));
   b.cub_temp_bytes = pair_sort_temp_bytes(D, 32 + tile_bits);
   b.cub_temp = c.take<char>(b.cub_temp_bytes);
   if (bytes) *bytes = c.bytes();
@@ -207,6 +226,10 @@ int b200gs_set_option(const char* name, int value) {
   g_err[0] = 0;
   if (name && !strcmp(name, "bin_shift")) {
     g_bin_shift_override.store(value < 0 ? -1 : (value > 5 ? 5 : value));
+    return 0;
+  }
+  if (name && !strcmp(name, "sort")) {
+    g_sort_mode.store(value < 0 ? 1 : (value > 2 ? 2 : value));
     return 0;
   }
   if (name && !strcmp(name, "gather")) {
@@ -315,11 +338,18 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
       return rc2;
     if (cap > 0) {
       if ((rc2 = check_cuda(cudaMemsetAsync(gb.counters, 0, 32 * sizeof(uint32_t), st), "clear counters"))) return rc2;
+      const int key_bits = 32 + tile_bits;
+      const bool coop = use_coop_sort(cap);
+      // the cooperative sort ping-pongs (passes) times; emit into whichever buffer makes the
+      // result land in keys_sorted / vals_sorted
+      const bool emit_into_sorted = coop && (((key_bits + 7) / 8) % 2 == 0);
+      uint64_t* emit_keys = emit_into_sorted ? bb.keys_sorted : bb.keys;
+      uint32_t* emit_vals = emit_into_sorted ? bb.vals_sorted : bb.vals;
       EmitArgs ea;
       ea.P = P; ea.gx = gx; ea.gy = gy; ea.gbx = gbx; ea.bin_shift = bs;
       ea.invalid_tile = (uint32_t)num_tiles; ea.capacity = cap;
       ea.tiles = gb.tiles; ea.offsets = gb.offsets; ea.depth_key = gb.depth_key; ea.rec = gb.rec; ea.radii = radii;
-      ea.keys = bb.keys; ea.vals = bb.vals;
+      ea.keys = emit_keys; ea.vals = emit_vals;
       ea.big_queue = gb.big_queue; ea.big_count = gb.counters;
       {
         StageTimer t(2, st);
@@ -328,7 +358,14 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
       if ((rc2 = debug_sync(prm, st, "emit pairs"))) return rc2;
       {
         StageTimer t(3, st);
-        if ((rc2 = sort_pairs(bb, cap, 32 + tile_bits, st))) return rc2;
+        if (coop) {
+          uint64_t* other_keys = emit_into_sorted ? bb.keys : bb.keys_sorted;
+          uint32_t* other_vals = emit_into_sorted ? bb.vals : bb.vals_sorted;
+          if ((rc2 = coop_sort_pairs(emit_keys, emit_vals, other_keys, other_vals, bb.coop_hist, cap, key_bits, st)))
+            return rc2;
+        } else if ((rc2 = sort_pairs(bb, cap, key_bits, st))) {
+          return rc2;
+        }
       }
       if ((rc2 = debug_sync(prm, st, "pair sort"))) return rc2;
       RangesArgs ga;

@@ -52,6 +52,7 @@ struct BinBuf {
   uint64_t* keys_sorted; // [D]
   uint64_t* keys;        // [D] (bin << 32) | depth bits, emission (index) order
   uint32_t* vals;        // [D] Gaussian ids
+  uint32_t* coop_hist;   // rotating digit histograms of the cooperative sort
   char* cub_temp;
   size_t cub_temp_bytes;
 };

@@ -82,6 +82,13 @@ void launch_render_bwd(const RenderBwdArgs& a, cudaStream_t st);
 void set_gather_mode(int mode);  // 0: TMA bulk copy per record, 1: LDGSTS
 void launch_export_rgb8(const float* color, int H, int W, uint8_t* out, cudaStream_t st);
 
+// coopsort.cu: single-launch cooperative radix sort for small pair lists
+constexpr int COOP_SORT_MAX_BLOCKS = 256;
+constexpr int64_t COOP_SORT_MAX_ITEMS = 3 * 1000 * 1000;
+size_t coop_sort_hist_bytes();
+int coop_sort_pairs(uint64_t* keys0, uint32_t* vals0, uint64_t* keys1, uint32_t* vals1, uint32_t* hist, uint32_t n,
+                    int key_bits, cudaStream_t st);
+
 // scene.cu
 int launch_ply_activate(int P, const float* v, const B200GSPlyLayout& L, float* means, float* shs, float* opac,
                         float* scales, float* rots, cudaStream_t st);

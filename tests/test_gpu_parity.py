@@ -232,25 +232,28 @@ def test_export_rgb8_matches_numpy():
         assert (out != ref).mean() < 1e-3       # only exact .5 ties may differ
 
 
-def test_bin_shift_and_gather_mode_never_change_results():
-    """Tuning knobs: every bin size (16..512 px) and both record-gather modes give bit-identical
-    images and radii, and the same gradients up to atomic-order noise."""
+def test_bin_shift_gather_and_sort_modes_never_change_results():
+    """Tuning knobs: every bin size (16..512 px), both record-gather modes and both pair-sort
+    implementations (cooperative single-launch radix sort / CUB) give bit-identical images and
+    radii, and the same gradients up to atomic-order noise."""
     from robosimgs_b200 import _cabi
     sc, cam, rs = small_scene(P=5000, degree=2, W=400, H=300)
     w = torch.rand(3, 300, 400, generator=torch.Generator().manual_seed(17))
     base = None
     try:
-        for gather in (1, 0):
+        for gather, sort in ((1, 2), (0, 2), (1, 0)):
             for shift in (0, 1, 2, 3, 5):
                 _cabi.set_option("gather", gather)
+                _cabi.set_option("sort", sort)
                 _cabi.set_option("bin_shift", shift)
                 color, radii, grads = gpu_render(sc, cam, 2, bg=(0.2, 0.1, 0.4), grad_weight=w)
                 if base is None:
                     base = (color, radii, grads)
                     continue
-                assert np.array_equal(color, base[0]) and np.array_equal(radii, base[1]), (gather, shift)
+                assert np.array_equal(color, base[0]) and np.array_equal(radii, base[1]), (gather, sort, shift)
                 for k in ("means3D", "shs", "opacities", "scales", "rotations"):
-                    assert max_rel_err(grads[k], base[2][k]) < 1e-5, (gather, shift, k)
+                    assert max_rel_err(grads[k], base[2][k]) < 1e-5, (gather, sort, shift, k)
     finally:
         _cabi.set_option("gather", 1)
+        _cabi.set_option("sort", 1)
         _cabi.set_option("bin_shift", -1)
