@@ -57,6 +57,8 @@ typedef struct B200GSParams {
   float scale_modifier;
   int32_t prefiltered;    /* accepted for signature parity; culled Gaussians are simply skipped */
   int32_t debug;          /* !=0: synchronise and check for errors after every kernel */
+  float near_plane;       /* near cull on view-space z; <= 0 selects the public default 0.2 */
+  int32_t reserved0;
   int64_t pair_capacity_hint; /* 0: size the binning buffer exactly (host waits for D before
                                  launching the binning stage, as the replaced interface does).
                                  >0: launch the whole frame for this many (Gaussian,tile) pair
@@ -118,6 +120,11 @@ int b200gs_backward(const B200GSParams* prm, const float* bg, const float* viewm
 /* present[i] = 1 iff Gaussian i passes the near-plane cull (view-space z > 0.2). */
 int b200gs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
                         const float* projmatrix, uint8_t* present, void* stream);
+
+/* out_alpha[H][W] = 1 - final transmittance of the forward call that produced `img` (the opacity
+ * image a gsplat-style caller expects next to the colour). */
+int b200gs_extract_alpha(const char* img, int32_t image_height, int32_t image_width, float* out_alpha,
+                         void* stream);
 
 /* Frame export for the datagen sweep: color[3][H][W] fp32 -> out_hwc[H][W][3] 8-bit RGB
  * (clamp to [0,1], *255, round to nearest).  The reference's per-frame scene render feeds image

@@ -54,6 +54,7 @@ def _params_struct(real):
         _fields_ = [
             ("P", C.c_int), ("sh_degree", C.c_int), ("M", C.c_int), ("H", C.c_int), ("W", C.c_int),
             ("tanfovx", real), ("tanfovy", real), ("scale_modifier", real), ("denom_eps", real),
+            ("near_plane", real),
             ("bg", real * 3), ("view", real * 16), ("proj", real * 16), ("campos", real * 3),
         ]
     return P
@@ -76,7 +77,7 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def make_params(settings, P, M, dtype=np.float32, denom_eps=1e-7):
+def make_params(settings, P, M, dtype=np.float32, denom_eps=1e-7, near_plane=0.2):
     """settings: any object with the GaussianRasterizationSettings field names."""
     S = _PF32 if dtype == np.float32 else _PF64
     p = S()
@@ -85,6 +86,7 @@ def make_params(settings, P, M, dtype=np.float32, denom_eps=1e-7):
     p.tanfovx, p.tanfovy = float(settings.tanfovx), float(settings.tanfovy)
     p.scale_modifier = float(settings.scale_modifier)
     p.denom_eps = float(denom_eps)
+    p.near_plane = float(near_plane)
     bg = _np(settings.bg, np.float64).reshape(-1)
     vm = _np(settings.viewmatrix, np.float64).reshape(-1)
     pm = _np(settings.projmatrix, np.float64).reshape(-1)
@@ -99,7 +101,7 @@ def make_params(settings, P, M, dtype=np.float32, denom_eps=1e-7):
 
 
 def forward(settings, means3D, opacities, shs=None, colors_precomp=None, scales=None,
-            rotations=None, cov3D_precomp=None, dtype=np.float32, denom_eps=1e-7):
+            rotations=None, cov3D_precomp=None, dtype=np.float32, denom_eps=1e-7, near_plane=0.2):
     """Full oracle forward.  Returns a namespace with the image, radii and every intermediate."""
     L = lib()
     sfx = "_f32" if dtype == np.float32 else "_f64"
@@ -112,7 +114,7 @@ def forward(settings, means3D, opacities, shs=None, colors_precomp=None, scales=
     P = means.shape[0]
     shs_ = _np(shs, dtype)
     M = 0 if shs_ is None else (shs_.shape[1] if shs_.ndim == 3 else shs_.reshape(P, -1, 3).shape[1])
-    prm = make_params(settings, P, M, dtype, denom_eps)
+    prm = make_params(settings, P, M, dtype, denom_eps, near_plane)
     H, W = prm.H, prm.W
     st = SimpleNamespace(dtype=dtype, P=P, M=M, H=H, W=W, params=prm, sfx=sfx)
     st.means, st.shs = means, shs_

@@ -36,6 +36,7 @@ typedef struct {
   int H, W;
   REAL tanfovx, tanfovy, scale_modifier;
   REAL denom_eps; /* regulariser in the conic adjoint; 1e-7 in the public implementation */
+  REAL near_plane; /* near cull on view-space z; 0.2 in the public implementation */
   REAL bg[3];
   REAL view[16];
   REAL proj[16];
@@ -178,7 +179,7 @@ int FN(gso_preprocess)(const PARAMS* p, const REAL* means, const REAL* shs,
     const REAL* pm = p->proj;
     /* step 1: near cull on view-space z */
     REAL vz = v[2] * mu[0] + v[6] * mu[1] + v[10] * mu[2] + v[14];
-    if (vz <= (REAL)0.2) continue;
+    if (vz <= p->near_plane) continue;
     /* step 2 */
     REAL hx = pm[0] * mu[0] + pm[4] * mu[1] + pm[8] * mu[2] + pm[12];
     REAL hy = pm[1] * mu[0] + pm[5] * mu[1] + pm[9] * mu[2] + pm[13];

@@ -16,6 +16,7 @@ EXPORTED_SYMBOLS = (
     "b200gs_last_error", "b200gs_version", "b200gs_launch_count",
     "b200gs_profile_enable", "b200gs_profile_read", "b200gs_stage_name", "b200gs_export_rgb8",
     "b200gs_set_option", "b200gs_ply_activate", "b200gs_transform_gaussians",
+    "b200gs_extract_alpha",
 )
 NUM_STAGES = 8
 
@@ -25,7 +26,8 @@ class B200GSParams(C.Structure):
         ("P", C.c_int32), ("sh_degree", C.c_int32), ("M", C.c_int32),
         ("image_height", C.c_int32), ("image_width", C.c_int32),
         ("tanfovx", C.c_float), ("tanfovy", C.c_float), ("scale_modifier", C.c_float),
-        ("prefiltered", C.c_int32), ("debug", C.c_int32), ("pair_capacity_hint", C.c_int64),
+        ("prefiltered", C.c_int32), ("debug", C.c_int32), ("near_plane", C.c_float), ("reserved0", C.c_int32),
+        ("pair_capacity_hint", C.c_int64),
     ]
 
 
@@ -83,6 +85,8 @@ def lib():
     L.b200gs_ply_activate.argtypes = [C.c_int32, fp, C.POINTER(B200GSPlyLayout), fp, fp, fp, fp, fp, vp]
     L.b200gs_transform_gaussians.restype = C.c_int
     L.b200gs_transform_gaussians.argtypes = [C.c_int32, fp, fp, vp, fp, fp, C.c_int32, fp, fp, vp]
+    L.b200gs_extract_alpha.restype = C.c_int
+    L.b200gs_extract_alpha.argtypes = [vp, C.c_int32, C.c_int32, fp, vp]
     L.b200gs_set_option.restype = C.c_int
     L.b200gs_set_option.argtypes = [C.c_char_p, C.c_int]
     L.b200gs_profile_enable.argtypes = [C.c_int]

@@ -310,6 +310,7 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
   pa.P = P; pa.M = prm->M; pa.W = W; pa.H = H; pa.gx = gx; pa.gy = gy; pa.bin_shift = bs;
   pa.sh_vec = (shs && (prm->M & 3) == 0 && (reinterpret_cast<uintptr_t>(shs) & 15) == 0) ? 1 : 0;
   pa.tanfovx = prm->tanfovx; pa.tanfovy = prm->tanfovy; pa.scale_modifier = prm->scale_modifier;
+  pa.near_plane = prm->near_plane > 0.f ? prm->near_plane : 0.2f;
   pa.means = means3D; pa.scales = scales; pa.rots = rotations; pa.opac = opacities; pa.shs = shs;
   pa.colors_precomp = colors_precomp; pa.cov3d_precomp = cov3D_precomp;
   pa.view = viewmatrix; pa.proj = projmatrix; pa.campos = campos;
@@ -492,6 +493,17 @@ int b200gs_backward(const B200GSParams* prm, const float* bg, const float* viewm
   return debug_sync(prm, st, "project backward");
 }
 
+int b200gs_extract_alpha(const char* img, int32_t H, int32_t W, float* out_alpha, void* stream) {
+  g_err[0] = 0;
+  if (!img || !out_alpha || H <= 0 || W <= 0) {
+    set_error("extract_alpha: invalid arguments");
+    return B200GS_ERR_INVALID_ARG;
+  }
+  ImgBuf ib = carve_img(const_cast<char*>(img), H, W, nullptr);
+  launch_extract_alpha(ib.pix, (size_t)H * W, out_alpha, static_cast<cudaStream_t>(stream));
+  return check_cuda(cudaGetLastError(), "extract_alpha");
+}
+
 int b200gs_export_rgb8(const float* color, int32_t H, int32_t W, uint8_t* out_hwc, void* stream) {
   g_err[0] = 0;
   if (!color || !out_hwc || H <= 0 || W <= 0) {
@@ -550,7 +562,7 @@ int b200gs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix
     return B200GS_ERR_INVALID_ARG;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  launch_mark_visible(P, means3D, viewmatrix, present, st);
+  launch_mark_visible(P, means3D, viewmatrix, 0.2f, present, st);
   return check_cuda(cudaGetLastError(), "mark_visible");
 }
 

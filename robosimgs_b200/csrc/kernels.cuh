@@ -6,7 +6,7 @@ namespace b200gs {
 
 struct ProjectArgs {
   int P, M, W, H, gx, gy, sh_vec, bin_shift;
-  float tanfovx, tanfovy, scale_modifier;
+  float tanfovx, tanfovy, scale_modifier, near_plane;
   const float *means, *scales, *rots, *opac, *shs, *colors_precomp, *cov3d_precomp;
   const float *view, *proj, *campos;
   int32_t* radii;
@@ -75,7 +75,9 @@ struct ProjectBwdArgs {
 void launch_project(const ProjectArgs& a, int deg, cudaStream_t st);
 void launch_emit_pairs(const EmitArgs& a, cudaStream_t st);
 void launch_tile_ranges(const RangesArgs& a, cudaStream_t st);
-void launch_mark_visible(int P, const float* means, const float* view, uint8_t* present, cudaStream_t st);
+void launch_mark_visible(int P, const float* means, const float* view, float near_plane, uint8_t* present,
+                         cudaStream_t st);
+void launch_extract_alpha(const float4* pix, size_t npx, float* out, cudaStream_t st);
 void launch_project_bwd(const ProjectBwdArgs& a, int deg, cudaStream_t st);
 void launch_render(const RenderArgs& a, cudaStream_t st);
 void launch_render_bwd(const RenderBwdArgs& a, cudaStream_t st);

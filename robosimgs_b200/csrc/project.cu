@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(256, PROJECT_MIN_BLOCKS) k_project(ProjectArgs
 
   const float3 mu = make_float3(__ldg(a.means + 3 * i), __ldg(a.means + 3 * i + 1), __ldg(a.means + 3 * i + 2));
   const float vz = c.v[2] * mu.x + c.v[6] * mu.y + c.v[10] * mu.z + c.v[14];
-  if (vz > 0.2f) {
+  if (vz > a.near_plane) {
     const float hx = c.p[0] * mu.x + c.p[4] * mu.y + c.p[8] * mu.z + c.p[12];
     const float hy = c.p[1] * mu.x + c.p[5] * mu.y + c.p[9] * mu.z + c.p[13];
     const float hw = c.p[3] * mu.x + c.p[7] * mu.y + c.p[11] * mu.z + c.p[15];
@@ -498,12 +498,12 @@ __global__ void __launch_bounds__(256) k_tile_ranges(RangesArgs a) {
 // K10: near-plane visibility
 // ==================================================================================================
 __global__ void k_mark_visible(int P, const float* __restrict__ means, const float* __restrict__ view,
-                               uint8_t* __restrict__ present) {
+                               float near_plane, uint8_t* __restrict__ present) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P) return;
   const float vz = __ldg(view + 2) * means[3 * i] + __ldg(view + 6) * means[3 * i + 1] +
                    __ldg(view + 10) * means[3 * i + 2] + __ldg(view + 14);
-  present[i] = vz > 0.2f ? 1 : 0;
+  present[i] = vz > near_plane ? 1 : 0;
 }
 
 // ==================================================================================================
@@ -783,9 +783,21 @@ void launch_tile_ranges(const RangesArgs& a, cudaStream_t st) {
   count_launch();
 }
 
-void launch_mark_visible(int P, const float* means, const float* view, uint8_t* present, cudaStream_t st) {
+void launch_mark_visible(int P, const float* means, const float* view, float near_plane, uint8_t* present,
+                         cudaStream_t st) {
   if (P == 0) return;
-  k_mark_visible<<<(P + 255) / 256, 256, 0, st>>>(P, means, view, present);
+  k_mark_visible<<<(P + 255) / 256, 256, 0, st>>>(P, means, view, near_plane, present);
+  count_launch();
+}
+
+__global__ void k_extract_alpha(const float4* __restrict__ pix, size_t npx, float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < npx) out[i] = 1.f - pix[i].w;
+}
+
+void launch_extract_alpha(const float4* pix, size_t npx, float* out, cudaStream_t st) {
+  if (npx == 0) return;
+  k_extract_alpha<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(pix, npx, out);
   count_launch();
 }
 

@@ -146,16 +146,16 @@ _PAIR_HINTS: dict = {}
 SPECULATE_PAIR_CAPACITY = True
 
 
-def _params(P, M, rs: GaussianRasterizationSettings, hint: int = 0) -> _cabi.B200GSParams:
+def _params(P, M, rs: GaussianRasterizationSettings, hint: int = 0, near_plane: float = 0.0) -> _cabi.B200GSParams:
     return _cabi.B200GSParams(int(P), int(rs.sh_degree), int(M), int(rs.image_height), int(rs.image_width),
                               float(rs.tanfovx), float(rs.tanfovy), float(rs.scale_modifier),
-                              int(bool(rs.prefiltered)), int(bool(rs.debug)), int(hint))
+                              int(bool(rs.prefiltered)), int(bool(rs.debug)), float(near_plane), 0, int(hint))
 
 
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
-                cov3Ds_precomp, raster_settings, grad_mode=True):
+                cov3Ds_precomp, raster_settings, grad_mode=True, near_plane=0.0, want_alpha=False):
         L = _cabi.lib()
         rs = raster_settings
         if getattr(rs, "antialiasing", False):
@@ -180,7 +180,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         H, W = int(rs.image_height), int(rs.image_width)
         hint_key = (dev.index, P, H, W)
         last_D = _PAIR_HINTS.get(hint_key, 0) if SPECULATE_PAIR_CAPACITY and not rs.debug else 0
-        prm = _params(P, M, rs, last_D + (last_D >> 4) + 32768 if last_D > 0 else 0)
+        prm = _params(P, M, rs, last_D + (last_D >> 4) + 32768 if last_D > 0 else 0, near_plane)
         color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
         radii = torch.empty((P,), dtype=torch.int32, device=dev)
         num_rendered = C.c_int32(0)
@@ -192,7 +192,13 @@ class _RasterizeGaussians(torch.autograd.Function):
                 _ptr(colors_precomp), _ptr(opacities), _ptr(scales), _ptr(rotations),
                 _ptr(cov3Ds_precomp), _ptr(color), _ptr(radii), lease.allocs["geom"], lease.allocs["binning"],
                 lease.allocs["img"], C.byref(num_rendered), stream))
+            alpha = None
+            if want_alpha:
+                alpha = torch.empty((H, W), dtype=torch.float32, device=dev)
+                _cabi.check(L.b200gs_extract_alpha(_ptr(lease.tensor("img")), C.c_int32(H), C.c_int32(W),
+                                                   _ptr(alpha), stream))
         ctx.raster_settings = rs
+        ctx.near_plane = near_plane
         ctx.num_rendered = int(num_rendered.value)
         _PAIR_HINTS[hint_key] = ctx.num_rendered
         ctx.M = M
@@ -208,10 +214,13 @@ class _RasterizeGaussians(torch.autograd.Function):
         else:
             lease.release()        # forward-only: the next call on this stream may reuse the scratch
         ctx.mark_non_differentiable(radii)
+        if want_alpha:
+            ctx.mark_non_differentiable(alpha)
+            return color, radii, alpha
         return color, radii
 
     @staticmethod
-    def backward(ctx, grad_out_color, _grad_radii):
+    def backward(ctx, grad_out_color, _grad_radii, *_unused):
         L = _cabi.lib()
         rs = ctx.raster_settings
         (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, radii, geom,
@@ -232,7 +241,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         g_scales = e(P, 3) if has_sr else None
         g_rots = e(P, 4) if has_sr else None
         g_cov = e(P, 6) if has_cov else None
-        prm = _params(P, ctx.M, rs)
+        prm = _params(P, ctx.M, rs, 0, ctx.near_plane)
         with torch.cuda.device(dev):
             lease = _Lease(dev, ("scratch",))
             stream = C.c_void_p(lease.stream)
@@ -246,7 +255,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             lease.release()
         # order of the public interface: means3D, means2D, sh, colors_precomp, opacities, scales,
         # rotations, cov3Ds_precomp, raster_settings
-        return g_means3D, g_means2D, g_sh, g_col, g_opac, g_scales, g_rots, g_cov, None, None
+        return g_means3D, g_means2D, g_sh, g_col, g_opac, g_scales, g_rots, g_cov, None, None, None, None
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,

@@ -257,3 +257,46 @@ def test_bin_shift_gather_and_sort_modes_never_change_results():
         _cabi.set_option("gather", 1)
         _cabi.set_option("sort", 1)
         _cabi.set_option("bin_shift", -1)
+
+
+def test_gsplat_style_rasterization_shim_matches_oracle():
+    """gsplat signature (viewmats + Ks, near_plane 0.01, un-normalised quats, off-centre principal
+    point, alphas) mapped onto the same kernels; checked against the oracle run with the equivalent
+    inria-style settings."""
+    from oracle import gs_oracle
+    from robosimgs_b200.gsplat_compat import rasterization
+    from robosimgs_b200.rasterizer import GaussianRasterizationSettings
+    sc, cam, _ = small_scene(P=2500, degree=2, W=176, H=128, eye=(0.2, 0.1, 0.35), fov=70.0)   # splats inside 0.2
+    W, H = 176, 128
+    V = cam.viewmatrix.T.contiguous()                      # world->camera
+    fx = W / (2 * cam.tanfovx); fy = H / (2 * cam.tanfovy)
+    K = torch.tensor([[fx, 0, W / 2 + 7.25], [0, fy, H / 2 - 4.5], [0, 0, 1.0]])
+    scale_q = torch.rand(2500, 1, generator=torch.Generator().manual_seed(2)) + 0.5
+    dev = torch.device("cuda:0")
+    leaf = lambda t: t.to(dev).clone().requires_grad_(True)
+    means, quats, scales, opac, shs = leaf(sc.means3D), leaf(sc.rotations * scale_q), leaf(sc.scales), \
+        leaf(sc.opacities.reshape(-1)), leaf(sc.shs)
+    bgs = torch.tensor([[0.2, 0.1, 0.4]], device=dev)
+    colors, alphas, meta = rasterization(means, quats, scales, opac, shs, V[None].to(dev), K[None].to(dev), W, H,
+                                         sh_degree=2, backgrounds=bgs)
+    assert colors.shape == (1, H, W, 3) and alphas.shape == (1, H, W, 1) and meta["radii"].shape == (1, 2500)
+    w = torch.rand(H, W, 3, generator=torch.Generator().manual_seed(3))
+    (colors[0] * w.to(dev)).sum().backward()
+    # oracle with the equivalent settings
+    from robosimgs_b200.gsplat_compat import _camera_matrices
+    view_t, proj_t, campos, tfx, tfy = _camera_matrices(V, K, W, H, 0.01, 1000.0)
+    rs = GaussianRasterizationSettings(H, W, tfx, tfy, torch.tensor([0.2, 0.1, 0.4]), 1.0, view_t, proj_t, 2, campos,
+                                       False, False)
+    qn = (sc.rotations * scale_q) / (sc.rotations * scale_q).norm(dim=1, keepdim=True)
+    st = gs_oracle.forward(rs, sc.means3D, sc.opacities, shs=sc.shs, scales=sc.scales, rotations=qn,
+                           dtype=np.float64, near_plane=0.01)
+    assert ((st.depths > 0.01) & (st.depths < 0.2) & (st.radii > 0)).sum() > 10     # near-plane change matters
+    assert psnr(colors[0].detach().cpu().numpy().transpose(2, 0, 1), st.color) >= PSNR_MIN
+    assert np.abs(alphas[0, ..., 0].cpu().numpy() - (1 - st.final_T)).max() < 2e-3
+    ref = gs_oracle.backward(st, w.numpy().transpose(2, 0, 1))
+    assert max_rel_err(means.grad.cpu().numpy(), ref.means3D) < GRAD_TOL
+    assert max_rel_err(shs.grad.cpu().numpy(), ref.shs) < GRAD_TOL
+    assert max_rel_err(scales.grad.cpu().numpy(), ref.scales) < GRAD_TOL
+    with pytest.raises(NotImplementedError):
+        rasterization(means, quats, scales, opac, shs, V[None].to(dev), K[None].to(dev), W, H, sh_degree=2,
+                      render_mode="RGB+ED")
