@@ -174,6 +174,7 @@ def run_b200(args):
     ge.build()
     from robosimgs_b200 import GaussianRasterizer, _cabi, export_rgb8
     from robosimgs_b200.rasterizer import GaussianRasterizationSettings
+    from robosimgs_b200.losses import mse_loss as fused_mse_loss
     from robosimgs_b200.scenes import mse_loss, room_scene, room_target, settings_from_camera
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -267,21 +268,28 @@ def run_b200(args):
     m2 = torch.zeros_like(leaves["means3D"], requires_grad=True)
     rs_train = settings_from_camera(jittered_cameras(1, first=0)[0], SH_DEG, device=dev)
 
-    def train_step(_s):
-        for t in list(leaves.values()) + [m2]:
-            t.grad = None
-        col, _ = GaussianRasterizer(rs_train)(leaves["means3D"], m2, leaves["opacities"], shs=leaves["shs"],
-                                              scales=leaves["scales"], rotations=leaves["rotations"])
-        mse_loss(col, target).backward()
+    def make_train_step(loss_fn):
+        def train_step(_s):
+            for t in list(leaves.values()) + [m2]:
+                t.grad = None
+            col, _ = GaussianRasterizer(rs_train)(leaves["means3D"], m2, leaves["opacities"], shs=leaves["shs"],
+                                                  scales=leaves["scales"], rotations=leaves["rotations"])
+            loss_fn(col, target).backward()
+        return train_step
 
+    train_step = make_train_step(fused_mse_loss)          # loss fused in libb200gs (2 launches)
+    train_step_eager = make_train_step(mse_loss)          # same loss as eager PyTorch ops (~8 launches)
     for s in range(max(Wm, 3) + 5):
         train_step(s)
+        train_step_eager(s)
+    _cabi.launch_count(reset=True)
     _cabi.profile_enable(True)
     _cabi.profile_read(reset=True)
     train_ms = timed(train_step, K)
     stages_train = _cabi.profile_read(reset=True)
     _cabi.profile_enable(False)
     launches_train = _cabi.launch_count(reset=True)
+    train_eager_ms = timed(train_step_eager, K)
     clocks = sampler.stop()
     del leaves, m2
 
@@ -358,7 +366,9 @@ def run_b200(args):
                          "(126 MB L2), no explicit flush" % (D * 64 / 1e6),
                    "frame_checksum": checksum},
         "train": {"iters_per_s": world * K / (train_ms * 1e-3), "ms_per_iter": train_ms / K,
-                  "what": "fwd + mean((img-target)^2) + bwd, C3 camera, per-GPU replicas (no gradient all-reduce)",
+                  "what": "fwd + mean((img-target)^2) + bwd, C3 camera, per-GPU replicas (no gradient all-reduce); "
+                          "loss fused in libb200gs (robosimgs_b200.losses.mse_loss)",
+                  "iters_per_s_eager_torch_loss": world * K / (train_eager_ms * 1e-3),
                   "gpu_launches": launches_train},
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": "Mpixels/s", "ms_per_step": e2e_ms / K,

@@ -161,6 +161,17 @@ int b200gs_transform_gaussians(int32_t n, const float* means_in, const float* ro
                                const float* link_quats, int32_t L, float* means_out, float* rots_out,
                                void* stream);
 
+/*
+ * Training-step neighbour: photometric loss between a rendered image and its
+ * target, n floats each (n % 4 == 0, 16-byte aligned).
+ *   forward : *out_sum = sum_i w_l2 (a_i-b_i)^2 + w_l1 |a_i-b_i|        (one pass, device scalar)
+ *   backward: dL_da_i  = *upstream * scale * (2 w_l2 (a_i-b_i) + w_l1 sign(a_i-b_i))
+ */
+int b200gs_photometric_loss(const float* a, const float* b, int64_t n, float w_l2, float w_l1, float* out_sum,
+                            void* stream);
+int b200gs_photometric_loss_backward(const float* a, const float* b, int64_t n, float w_l2, float w_l1,
+                                     float scale, const float* upstream, float* dL_da, void* stream);
+
 /* Sizes of the forward scratch buffers for given P, H, W (geom, img) and D (binning); lets a
  * caller pre-size arenas.  Any of the out pointers may be NULL. */
 int b200gs_buffer_sizes(int32_t P, int32_t image_height, int32_t image_width, int64_t D,

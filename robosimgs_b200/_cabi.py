@@ -16,7 +16,7 @@ EXPORTED_SYMBOLS = (
     "b200gs_last_error", "b200gs_version", "b200gs_launch_count",
     "b200gs_profile_enable", "b200gs_profile_read", "b200gs_stage_name", "b200gs_export_rgb8",
     "b200gs_set_option", "b200gs_ply_activate", "b200gs_transform_gaussians",
-    "b200gs_extract_alpha",
+    "b200gs_extract_alpha", "b200gs_photometric_loss", "b200gs_photometric_loss_backward",
 )
 NUM_STAGES = 8
 
@@ -85,6 +85,10 @@ def lib():
     L.b200gs_ply_activate.argtypes = [C.c_int32, fp, C.POINTER(B200GSPlyLayout), fp, fp, fp, fp, fp, vp]
     L.b200gs_transform_gaussians.restype = C.c_int
     L.b200gs_transform_gaussians.argtypes = [C.c_int32, fp, fp, vp, fp, fp, C.c_int32, fp, fp, vp]
+    L.b200gs_photometric_loss.restype = C.c_int
+    L.b200gs_photometric_loss.argtypes = [fp, fp, C.c_int64, C.c_float, C.c_float, fp, vp]
+    L.b200gs_photometric_loss_backward.restype = C.c_int
+    L.b200gs_photometric_loss_backward.argtypes = [fp, fp, C.c_int64, C.c_float, C.c_float, C.c_float, fp, fp, vp]
     L.b200gs_extract_alpha.restype = C.c_int
     L.b200gs_extract_alpha.argtypes = [vp, C.c_int32, C.c_int32, fp, vp]
     L.b200gs_set_option.restype = C.c_int

@@ -493,6 +493,35 @@ int b200gs_backward(const B200GSParams* prm, const float* bg, const float* viewm
   return debug_sync(prm, st, "project backward");
 }
 
+static int check_loss_args(const float* a, const float* b, int64_t n, const void* o) {
+  if (n < 0 || (n & 3) || (n > 0 && (!a || !b || !o)) || (reinterpret_cast<uintptr_t>(a) & 15) ||
+      (reinterpret_cast<uintptr_t>(b) & 15)) {
+    set_error("photometric_loss: need n %% 4 == 0 and 16-byte aligned non-NULL buffers");
+    return B200GS_ERR_INVALID_ARG;
+  }
+  return 0;
+}
+
+int b200gs_photometric_loss(const float* a, const float* b, int64_t n, float w_l2, float w_l1, float* out_sum,
+                            void* stream) {
+  g_err[0] = 0;
+  if (int rc = check_loss_args(a, b, n, out_sum)) return rc;
+  launch_photometric_loss(a, b, (size_t)n, w_l2, w_l1, out_sum, static_cast<cudaStream_t>(stream));
+  return check_cuda(cudaGetLastError(), "photometric_loss");
+}
+
+int b200gs_photometric_loss_backward(const float* a, const float* b, int64_t n, float w_l2, float w_l1,
+                                     float scale, const float* upstream, float* dL_da, void* stream) {
+  g_err[0] = 0;
+  if (int rc = check_loss_args(a, b, n, dL_da)) return rc;
+  if (!upstream || (reinterpret_cast<uintptr_t>(dL_da) & 15)) {
+    set_error("photometric_loss_backward: upstream NULL or dL_da misaligned");
+    return B200GS_ERR_INVALID_ARG;
+  }
+  launch_photometric_loss_bwd(a, b, (size_t)n, w_l2, w_l1, scale, upstream, dL_da, static_cast<cudaStream_t>(stream));
+  return check_cuda(cudaGetLastError(), "photometric_loss_backward");
+}
+
 int b200gs_extract_alpha(const char* img, int32_t H, int32_t W, float* out_alpha, void* stream) {
   g_err[0] = 0;
   if (!img || !out_alpha || H <= 0 || W <= 0) {

@@ -98,6 +98,11 @@ void launch_transform_gaussians(int n, const float* means_in, const float* rots_
                                 const float* T, const float* Q, int L, float* means_out, float* rots_out,
                                 cudaStream_t st);
 
+void launch_photometric_loss(const float* a, const float* b, size_t n, float w_l2, float w_l1, float* out,
+                             cudaStream_t st);
+void launch_photometric_loss_bwd(const float* a, const float* b, size_t n, float w_l2, float w_l1, float scale,
+                                 const float* upstream, float* g, cudaStream_t st);
+
 // binning.cu (CUB): temp-storage sizing, scan and pair sort
 size_t scan_temp_bytes(int P);
 size_t pair_sort_temp_bytes(int64_t D, int key_bits);

@@ -91,3 +91,18 @@ def test_transform_kernel_and_articulated_composite_match_oracle():
                                rotations=np.concatenate([bg.rotations.numpy(), r]), dtype=np.float64)
         assert psnr(color.cpu().numpy(), st.color) >= 60.0
         assert (radii[art.P_bg:] > 0).sum() > 100        # the object is in view
+
+
+def test_fused_photometric_loss_matches_torch():
+    from robosimgs_b200.losses import mse_loss, photometric_loss
+    g = torch.Generator().manual_seed(8)
+    a = torch.rand(3, 120, 160, generator=g).cuda().requires_grad_(True)
+    b = torch.rand(3, 120, 160, generator=g).cuda()
+    for fused, ref in ((lambda: mse_loss(a, b), lambda: ((a - b) ** 2).mean()),
+                       (lambda: photometric_loss(a, b, 0.3, 0.8), lambda: (0.3 * (a - b) ** 2 + 0.8 * (a - b).abs()).mean())):
+        a.grad = None
+        l1 = fused(); (l1 * 1.7).backward(); g1 = a.grad.clone()
+        a.grad = None
+        l2 = ref(); (l2 * 1.7).backward(); g2 = a.grad.clone()
+        assert abs(float(l1) - float(l2)) < 1e-6 * max(1.0, abs(float(l2)))
+        assert torch.allclose(g1, g2, rtol=1e-5, atol=1e-9)
