@@ -262,10 +262,11 @@ __device__ __forceinline__ void warp_reduce9(float (&v)[8], float& v8, int lane)
 
 // ==================================================================================================
 // K7: compositing adjoint.  Front-to-back replay (same traversal, same ring as the forward): with
-// running transmittance T_j and running prefix colour, the colour composited behind splat j is
-// S_j = C_final - prefix_j, so
+// running transmittance T_j and the running prefix of composited colour, the colour composited behind
+// splat j is S_j = C_final - prefix_j, so
 //   dL/dalpha_j = T_j * <c_j, g> - (<S_j, g> + T_final * <bg, g>) / (1 - alpha_j),   g = dL/dpixel
 // which is algebraically the back-to-front recursion of the public algorithm.
+// Only the projection of the prefix onto g is needed, so it is carried as one scalar.
 // ==================================================================================================
 template <int MODE>
 __global__ void __launch_bounds__(256) k_render_bwd(RenderBwdArgs a) {
@@ -300,9 +301,11 @@ __global__ void __launch_bounds__(256) k_render_bwd(RenderBwdArgs a) {
     gg = __ldg(a.dL_dpix + hw + pid);
     gb = __ldg(a.dL_dpix + 2 * hw + pid);
   }
-  // T_final * <bg, g>
-  const float bgterm = fin.w * (__ldg(a.bg) * gr + __ldg(a.bg + 1) * gg + __ldg(a.bg + 2) * gb);
-  float T = 1.f, Cr = 0.f, Cg = 0.f, Cb = 0.f;
+  // F = <C_final, g> + T_final * <bg, g>.  With R_j = sum_{k<=j} w_k <c_k, g> (a running scalar) the
+  // "colour behind splat j" term <S_j, g> + T_final <bg, g> is simply F - R_j.
+  const float F = fin.x * gr + fin.y * gg + fin.z * gb +
+                  fin.w * (__ldg(a.bg) * gr + __ldg(a.bg + 1) * gg + __ldg(a.bg + 2) * gb);
+  float T = 1.f, R = 0.f;
 
   for (uint32_t c = 0; c < nchunks; c++) {
     const int s = c & 1;
@@ -335,12 +338,10 @@ __global__ void __launch_bounds__(256) k_render_bwd(RenderBwdArgs a) {
         float v[8], v8;
         if (valid) {
           const float w = alpha * T;
-          Cr = __fmaf_rn(q2.x, w, Cr);
-          Cg = __fmaf_rn(q2.y, w, Cg);
-          Cb = __fmaf_rn(q2.z, w, Cb);
+          const float cg = q2.x * gr + q2.y * gg + q2.z * gb;
+          R = __fmaf_rn(w, cg, R);
           const float inv1ma = rcp_fast(1.f - alpha);
-          const float behind = (fin.x - Cr) * gr + (fin.y - Cg) * gg + (fin.z - Cb) * gb;
-          const float dL_dalpha = T * (q2.x * gr + q2.y * gg + q2.z * gb) - inv1ma * (behind + bgterm);
+          const float dL_dalpha = T * cg - inv1ma * (F - R);
           T = T * (1.f - alpha);
           // Per-splat factors (opacity, conic, 0.5*W/H) are uniform over the pixels, so only the raw
           // moments of m = G * dL/dalpha about the splat centre are reduced; k_project_bwd turns them

@@ -139,9 +139,10 @@ class _Lease:
             pass
 
 
-# Pair-capacity hints (see B200GSParams.pair_capacity_hint): the number of (Gaussian,tile) pairs of
-# the previous frame with the same (device, P, H, W), plus head-room.  Purely a performance hint --
-# the library redoes the binning stage exactly if a frame needs more.
+# Pair-capacity hints (see B200GSParams.pair_capacity_hint): a slowly decaying maximum of the pair
+# counts of recent frames with the same (device, P, H, W), plus head-room -- so both a smooth camera
+# path and random training views stay under the hint.  Purely a performance hint: the library redoes
+# the binning stage exactly if a frame needs more.
 _PAIR_HINTS: dict = {}
 SPECULATE_PAIR_CAPACITY = True
 
@@ -200,7 +201,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.raster_settings = rs
         ctx.near_plane = near_plane
         ctx.num_rendered = int(num_rendered.value)
-        _PAIR_HINTS[hint_key] = ctx.num_rendered
+        _PAIR_HINTS[hint_key] = max(ctx.num_rendered, int(last_D * 0.97))
         ctx.M = M
         ctx.present = (sh is not None, colors_precomp is not None, scales is not None,
                        cov3Ds_precomp is not None)

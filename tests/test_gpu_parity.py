@@ -213,7 +213,7 @@ def test_speculative_pair_capacity_paths_are_bit_identical():
             rasterizer._PAIR_HINTS[key] = hint
         color, radii = GaussianRasterizer(rs_gpu)(*args, **kw)
         outs.append((color.detach().cpu().numpy(), color.grad_fn.num_rendered))
-        assert rasterizer._PAIR_HINTS[key] == color.grad_fn.num_rendered
+        assert rasterizer._PAIR_HINTS[key] >= color.grad_fn.num_rendered
         w = torch.ones_like(color)
         (color * w).sum().backward()                       # backward works from every path
         assert torch.isfinite(args[0].grad).all()
