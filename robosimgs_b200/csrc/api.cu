@@ -102,6 +102,19 @@ static bool use_coop_sort(int64_t n) {
   return n <= (m == 2 ? COOP_SORT_MAX_ITEMS : COOP_SORT_AUTO_MAX);
 }
 
+// compositing kernels: 1 = four pixels per thread (render4.cu, default), 0 = one pixel per thread
+// (render.cu).  B200GS_RENDER=1px|4px or b200gs_set_option("render", 0|1).
+static std::atomic<int> g_render_mode{-1};
+static bool use_render4() {
+  int m = g_render_mode.load();
+  if (m < 0) {
+    const char* e = getenv("B200GS_RENDER");
+    m = (e && e[0] == '1') ? 0 : 1;
+    g_render_mode.store(m);
+  }
+  return m == 1;
+}
+
 static int tile_bits_for(int num_tiles) {
   int bits = 1;
   while ((1 << bits) <= num_tiles) bits++;  // room for the invalid id == num_tiles
@@ -230,6 +243,10 @@ int b200gs_set_option(const char* name, int value) {
   }
   if (name && !strcmp(name, "sort")) {
     g_sort_mode.store(value < 0 ? 1 : (value > 2 ? 2 : value));
+    return 0;
+  }
+  if (name && !strcmp(name, "render")) {
+    g_render_mode.store(value == 0 ? 0 : 1);
     return 0;
   }
   if (name && !strcmp(name, "gather")) {
@@ -381,9 +398,11 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
     ra.W = W; ra.H = H; ra.gbx = gbx; ra.bin_shift = bs; ra.ranges = ib.ranges; ra.point_list = bb.vals_sorted;
     ra.rec = gb.rec; ra.bg = bg; ra.out_color = out_color;
     ra.pix = ib.pix; ra.n_contrib = ib.n_contrib;
+    ra.vec4 = ((W & 3) == 0 && (reinterpret_cast<uintptr_t>(out_color) & 15) == 0) ? 1 : 0;
     {
       StageTimer t(5, st);
-      launch_render(ra, st);
+      if (use_render4()) launch_render4(ra, st);
+      else launch_render(ra, st);
     }
     return debug_sync(prm, st, "render");
   };
@@ -469,9 +488,11 @@ int b200gs_backward(const B200GSParams* prm, const float* bg, const float* viewm
     ra.W = W; ra.H = H; ra.gbx = gbx; ra.bin_shift = bs; ra.ranges = ib.ranges; ra.point_list = bb.vals_sorted;
     ra.rec = gb.rec; ra.bg = bg; ra.pix = ib.pix;
     ra.n_contrib = ib.n_contrib; ra.dL_dpix = dL_dout_color; ra.grad2d = grad2d;
+    ra.vec4 = ((W & 3) == 0 && (reinterpret_cast<uintptr_t>(dL_dout_color) & 15) == 0) ? 1 : 0;
     {
       StageTimer t(6, st);
-      launch_render_bwd(ra, st);
+      if (use_render4()) launch_render_bwd4(ra, st);
+      else launch_render_bwd(ra, st);
     }
     if ((rc = debug_sync(prm, st, "render backward"))) return rc;
   }

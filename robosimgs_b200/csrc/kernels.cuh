@@ -38,6 +38,7 @@ struct RangesArgs {
 
 struct RenderArgs {
   int W, H, gbx, bin_shift;
+  int vec4;                    // W % 4 == 0 and out_color 16-byte aligned: 128-bit pixel stores
   const uint2* ranges;
   const uint32_t* point_list;  // Gaussian ids in (tile, depth) order
   const float4* rec;           // [P] projected-splat records
@@ -49,6 +50,7 @@ struct RenderArgs {
 
 struct RenderBwdArgs {
   int W, H, gbx, bin_shift;
+  int vec4;                    // W % 4 == 0 and dL_dpix 16-byte aligned: 128-bit pixel loads
   const uint2* ranges;
   const uint32_t* point_list;
   const float4* rec;
@@ -82,6 +84,9 @@ void launch_project_bwd(const ProjectBwdArgs& a, int deg, cudaStream_t st);
 void launch_render(const RenderArgs& a, cudaStream_t st);
 void launch_render_bwd(const RenderBwdArgs& a, cudaStream_t st);
 void set_gather_mode(int mode);  // 0: TMA bulk copy per record, 1: LDGSTS
+// render4.cu: four pixels per thread (default); render.cu keeps the one-pixel-per-thread kernels
+void launch_render4(const RenderArgs& a, cudaStream_t st);
+void launch_render_bwd4(const RenderBwdArgs& a, cudaStream_t st);
 void launch_export_rgb8(const float* color, int H, int W, uint8_t* out, cudaStream_t st);
 
 // coopsort.cu: single-launch cooperative radix sort for small pair lists
