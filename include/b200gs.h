@@ -172,6 +172,38 @@ int b200gs_photometric_loss(const float* a, const float* b, int64_t n, float w_l
 int b200gs_photometric_loss_backward(const float* a, const float* b, int64_t n, float w_l2, float w_l1,
                                      float scale, const float* upstream, float* dL_da, void* stream);
 
+/*
+ * Training-step neighbour: SSIM between a rendered image img1 and its target
+ * img2, both [C][H][W] fp32 -- the definition every public 3DGS trainer uses (11x11 Gaussian window,
+ * sigma 1.5, zero padding, C1 = 0.01^2, C2 = 0.03^2, per channel; the loss uses the mean of the map).
+ *   forward : *out_sum = sum of the SSIM map over C*H*W (device scalar).  If maps != NULL
+ *             ([3][C][H][W] floats) the three derivative maps the backward pass needs are stored.
+ *   backward: dL_dimg1 = *upstream * scale * d(sum of the SSIM map)/d(img1), from the stored maps.
+ */
+int b200gs_ssim_forward(const float* img1, const float* img2, int32_t C, int32_t H, int32_t W, float* maps,
+                        float* out_sum, void* stream);
+int b200gs_ssim_backward(const float* img1, const float* img2, const float* maps, int32_t C, int32_t H, int32_t W,
+                         float scale, const float* upstream, float* dL_dimg1, void* stream);
+
+/*
+ * Training-step neighbour: one fused Adam step over up to
+ * B200GS_ADAM_MAX_GROUPS parameter tensors in ONE launch (torch.optim.Adam semantics, no weight
+ * decay, no amsgrad): m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
+ *   p -= lr / (1 - b1^step) * m / (sqrt(v) / sqrt(1 - b2^step) + eps).   step counts from 1.
+ */
+#define B200GS_ADAM_MAX_GROUPS 8
+typedef struct B200GSAdamGroup {
+  float* param;          /* [n] updated in place */
+  const float* grad;     /* [n] */
+  float* exp_avg;        /* [n] first moment, updated in place */
+  float* exp_avg_sq;     /* [n] second moment, updated in place */
+  int64_t n;
+  float lr;              /* learning rate of this tensor (3DGS uses one per parameter kind) */
+  float reserved;
+} B200GSAdamGroup;
+int b200gs_adam_step(const B200GSAdamGroup* groups, int32_t num_groups, float beta1, float beta2, float eps,
+                     int32_t step, void* stream);
+
 /* Sizes of the forward scratch buffers for given P, H, W (geom, img) and D (binning); lets a
  * caller pre-size arenas.  Any of the out pointers may be NULL. */
 int b200gs_buffer_sizes(int32_t P, int32_t image_height, int32_t image_width, int64_t D,

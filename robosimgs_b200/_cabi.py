@@ -17,7 +17,9 @@ EXPORTED_SYMBOLS = (
     "b200gs_profile_enable", "b200gs_profile_read", "b200gs_stage_name", "b200gs_export_rgb8",
     "b200gs_set_option", "b200gs_ply_activate", "b200gs_transform_gaussians",
     "b200gs_extract_alpha", "b200gs_photometric_loss", "b200gs_photometric_loss_backward",
+    "b200gs_ssim_forward", "b200gs_ssim_backward", "b200gs_adam_step",
 )
+ADAM_MAX_GROUPS = 8
 NUM_STAGES = 8
 
 
@@ -34,6 +36,11 @@ class B200GSParams(C.Structure):
 class B200GSPlyLayout(C.Structure):
     _fields_ = [("stride", C.c_int32), ("off_xyz", C.c_int32), ("off_fdc", C.c_int32), ("off_frest", C.c_int32),
                 ("n_rest", C.c_int32), ("off_opacity", C.c_int32), ("off_scale", C.c_int32), ("off_rot", C.c_int32)]
+
+
+class B200GSAdamGroup(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("n", C.c_int64), ("lr", C.c_float), ("reserved", C.c_float)]
 
 
 RESIZE_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
@@ -89,6 +96,13 @@ def lib():
     L.b200gs_photometric_loss.argtypes = [fp, fp, C.c_int64, C.c_float, C.c_float, fp, vp]
     L.b200gs_photometric_loss_backward.restype = C.c_int
     L.b200gs_photometric_loss_backward.argtypes = [fp, fp, C.c_int64, C.c_float, C.c_float, C.c_float, fp, fp, vp]
+    L.b200gs_ssim_forward.restype = C.c_int
+    L.b200gs_ssim_forward.argtypes = [fp, fp, C.c_int32, C.c_int32, C.c_int32, fp, fp, vp]
+    L.b200gs_ssim_backward.restype = C.c_int
+    L.b200gs_ssim_backward.argtypes = [fp, fp, fp, C.c_int32, C.c_int32, C.c_int32, C.c_float, fp, fp, vp]
+    L.b200gs_adam_step.restype = C.c_int
+    L.b200gs_adam_step.argtypes = [C.POINTER(B200GSAdamGroup), C.c_int32, C.c_float, C.c_float, C.c_float,
+                                   C.c_int32, vp]
     L.b200gs_extract_alpha.restype = C.c_int
     L.b200gs_extract_alpha.argtypes = [vp, C.c_int32, C.c_int32, fp, vp]
     L.b200gs_set_option.restype = C.c_int

@@ -543,6 +543,47 @@ int b200gs_photometric_loss_backward(const float* a, const float* b, int64_t n, 
   return check_cuda(cudaGetLastError(), "photometric_loss_backward");
 }
 
+int b200gs_ssim_forward(const float* img1, const float* img2, int32_t C, int32_t H, int32_t W, float* maps,
+                        float* out_sum, void* stream) {
+  g_err[0] = 0;
+  if (!img1 || !img2 || !out_sum || C <= 0 || C > 65535 || H <= 0 || W <= 0) {
+    set_error("ssim_forward: invalid arguments");
+    return B200GS_ERR_INVALID_ARG;
+  }
+  launch_ssim_fwd(img1, img2, C, H, W, maps, out_sum, static_cast<cudaStream_t>(stream));
+  return check_cuda(cudaGetLastError(), "ssim_forward");
+}
+
+int b200gs_ssim_backward(const float* img1, const float* img2, const float* maps, int32_t C, int32_t H, int32_t W,
+                         float scale, const float* upstream, float* dL_dimg1, void* stream) {
+  g_err[0] = 0;
+  if (!img1 || !img2 || !maps || !upstream || !dL_dimg1 || C <= 0 || C > 65535 || H <= 0 || W <= 0) {
+    set_error("ssim_backward: invalid arguments");
+    return B200GS_ERR_INVALID_ARG;
+  }
+  launch_ssim_bwd(img1, img2, maps, C, H, W, scale, upstream, dL_dimg1, static_cast<cudaStream_t>(stream));
+  return check_cuda(cudaGetLastError(), "ssim_backward");
+}
+
+int b200gs_adam_step(const B200GSAdamGroup* groups, int32_t num_groups, float beta1, float beta2, float eps,
+                     int32_t step, void* stream) {
+  g_err[0] = 0;
+  if (!groups || num_groups < 0 || num_groups > B200GS_ADAM_MAX_GROUPS || step < 1 || !(beta1 >= 0.f && beta1 < 1.f) ||
+      !(beta2 >= 0.f && beta2 < 1.f)) {
+    set_error("adam_step: need 0..%d groups, step >= 1, betas in [0,1)", B200GS_ADAM_MAX_GROUPS);
+    return B200GS_ERR_INVALID_ARG;
+  }
+  for (int i = 0; i < num_groups; i++) {
+    const B200GSAdamGroup& g = groups[i];
+    if (g.n < 0 || (g.n > 0 && (!g.param || !g.grad || !g.exp_avg || !g.exp_avg_sq))) {
+      set_error("adam_step: group %d has a NULL tensor or negative size", i);
+      return B200GS_ERR_INVALID_ARG;
+    }
+  }
+  if (int rc = launch_adam(groups, num_groups, beta1, beta2, eps, step, static_cast<cudaStream_t>(stream))) return rc;
+  return check_cuda(cudaGetLastError(), "adam_step");
+}
+
 int b200gs_extract_alpha(const char* img, int32_t H, int32_t W, float* out_alpha, void* stream) {
   g_err[0] = 0;
   if (!img || !out_alpha || H <= 0 || W <= 0) {

@@ -108,6 +108,14 @@ void launch_photometric_loss(const float* a, const float* b, size_t n, float w_l
 void launch_photometric_loss_bwd(const float* a, const float* b, size_t n, float w_l2, float w_l1, float scale,
                                  const float* upstream, float* g, cudaStream_t st);
 
+// train.cu: fused SSIM and multi-tensor Adam
+void launch_ssim_fwd(const float* img1, const float* img2, int C, int H, int W, float* maps, float* out_sum,
+                     cudaStream_t st);
+void launch_ssim_bwd(const float* img1, const float* img2, const float* maps, int C, int H, int W, float scale,
+                     const float* upstream, float* dL_dimg1, cudaStream_t st);
+int launch_adam(const B200GSAdamGroup* groups, int num_groups, float beta1, float beta2, float eps, int step,
+                cudaStream_t st);
+
 // binning.cu (CUB): temp-storage sizing, scan and pair sort
 size_t scan_temp_bytes(int P);
 size_t pair_sort_temp_bytes(int64_t D, int key_bits);

@@ -21,6 +21,7 @@
 //    with the transposing butterfly of render.cu -- one reduction per 128 pixels instead of per 32.
 #include <atomic>
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -29,7 +30,7 @@ namespace b200gs {
 
 constexpr int R4_CH = 64;       // records per ring stage == threads per CTA
 #ifndef R4_STAGES_N
-#define R4_STAGES_N 3
+#define R4_STAGES_N 2
 #endif
 constexpr int R4_STAGES = R4_STAGES_N;
 constexpr int R4_THREADS = 64;
@@ -156,7 +157,13 @@ __device__ __forceinline__ Tile4 tile4_setup(int W, int H, int warp, int lane) {
 // ==================================================================================================
 // K6 (four pixels per thread)
 // ==================================================================================================
-__global__ void __launch_bounds__(R4_THREADS) k_render_fwd4(RenderArgs a) {
+#ifndef R4_FWD_MINB
+#define R4_FWD_MINB 16
+#endif
+#ifndef R4_BWD_MINB
+#define R4_BWD_MINB 12
+#endif
+__global__ void __launch_bounds__(R4_THREADS, R4_FWD_MINB) k_render_fwd4(RenderArgs a) {
   __shared__ __align__(128) float4 sm[R4_STAGES][R4_CH * REC_F4];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -171,14 +178,49 @@ __global__ void __launch_bounds__(R4_THREADS) k_render_fwd4(RenderArgs a) {
 
   // A finished pixel (transmittance test failed once, or outside the image) is marked by a NEGATIVE
   // transmittance: |T| stays the final transmittance, T * (1 - alpha) can never pass the 1e-4 test
-  // again, so the hot loop needs no separate flag.
+  // again, so the hot loop needs no separate flag.  nstop = list position of the record that
+  // finished the pixel (n if none did): nothing at or behind it contributes, and every record in
+  // front of it that the adjoint finds valid did contribute -- all the adjoint needs to know.
   float T[4], Cr[4], Cg[4], Cb[4];
-  uint32_t last[4];
+  uint32_t nstop[4];
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     T[i] = t.in[i] ? 1.f : -1.f;
-    Cr[i] = 0.f; Cg[i] = 0.f; Cb[i] = 0.f; last[i] = 0u;
+    Cr[i] = 0.f; Cg[i] = 0.f; Cb[i] = 0.f; nstop[i] = n;
   }
+
+  // One record against the thread's four pixels.  CLAMP = false when opacity <= 0.99: then
+  // min(0.99, o*G) is the identity for every pair that can pass the tests (G <= 1 when power <= 0).
+  // The accumulate is predicated, not selected: FSETP/FSEL/FMNMX share the half-rate ALU pipe, which
+  // co-limits this loop with the issue rate (ncu: math-pipe throttle).
+  auto eval = [&](const float4& q0, const float4& q1, const float4& q2, uint32_t pos, auto clamp_tag) {
+    constexpr bool CLAMP = decltype(clamp_tag)::value;
+    const RowTerms rt = row_terms(q0.z, q0.w, q1.x, q0.y - t.pyf);
+    bool stop[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const float dx = q0.x - t.pxf[i];
+      const float p2 = power2_of(rt, dx);
+      float alpha = q1.y * ex2_fast(p2);
+      if (CLAMP) alpha = fminf(0.99f, alpha);
+      const bool valid = p2 <= 0.f && alpha >= (1.f / 255.f);
+      const float test_T = T[i] * (1.f - alpha);
+      const bool upd = valid && test_T >= 0.0001f;
+      stop[i] = valid && !(test_T >= 0.0001f);
+      if (upd) {
+        const float w = alpha * T[i];
+        Cr[i] = __fmaf_rn(q2.x, w, Cr[i]);
+        Cg[i] = __fmaf_rn(q2.y, w, Cg[i]);
+        Cb[i] = __fmaf_rn(q2.z, w, Cb[i]);
+        T[i] = test_T;
+      }
+    }
+    if (stop[0] || stop[1] || stop[2] || stop[3]) {   // rare: at most once per pixel
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        if (stop[i] && T[i] > 0.f) { T[i] = -T[i]; nstop[i] = pos; }
+    }
+  };
 
   for (uint32_t c = 0; c < nchunks; c++) {
     ring.wait();
@@ -201,25 +243,9 @@ __global__ void __launch_bounds__(R4_THREADS) k_render_fwd4(RenderArgs a) {
         mask &= mask - 1;
         const uint32_t jj = base + b;
         const float4 q0 = st[jj * REC_F4], q1 = st[jj * REC_F4 + 1], q2 = st[jj * REC_F4 + 2];
-        const RowTerms rt = row_terms(q0.z, q0.w, q1.x, q0.y - t.pyf);
-        const uint32_t pos = c * R4_CH + jj + 1;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const float dx = q0.x - t.pxf[i];
-          const float p2 = power2_of(rt, dx);
-          const float alpha = fminf(0.99f, q1.y * ex2_fast(p2));
-          const bool valid = p2 <= 0.f && alpha >= (1.f / 255.f);
-          const float test_T = T[i] * (1.f - alpha);
-          const bool upd = valid && test_T >= 0.0001f;
-          // branch-free: the four pixel chains interleave and hide the MUFU latency
-          const float w = upd ? alpha * T[i] : 0.f;
-          Cr[i] = __fmaf_rn(q2.x, w, Cr[i]);
-          Cg[i] = __fmaf_rn(q2.y, w, Cg[i]);
-          Cb[i] = __fmaf_rn(q2.z, w, Cb[i]);
-          const float keep = valid ? -fabsf(T[i]) : T[i];   // valid but not accepted: pixel is finished
-          T[i] = upd ? test_T : keep;
-          last[i] = upd ? pos : last[i];
-        }
+        const uint32_t pos = c * R4_CH + jj;
+        if (q1.y > 0.99f) eval(q0, q1, q2, pos, std::true_type{});
+        else eval(q0, q1, q2, pos, std::false_type{});
       }
     }
     const int num_done = __syncthreads_count(fmaxf(fmaxf(T[0], T[1]), fmaxf(T[2], T[3])) < 0.f);
@@ -236,7 +262,7 @@ __global__ void __launch_bounds__(R4_THREADS) k_render_fwd4(RenderArgs a) {
     float4* pix = a.pix + pid;
 #pragma unroll
     for (int i = 0; i < 4; i++) pix[i] = make_float4(Cr[i], Cg[i], Cb[i], T[i]);
-    *reinterpret_cast<uint4*>(a.n_contrib + pid) = make_uint4(last[0], last[1], last[2], last[3]);
+    *reinterpret_cast<uint4*>(a.n_contrib + pid) = make_uint4(nstop[0], nstop[1], nstop[2], nstop[3]);
     const float b0 = __ldg(a.bg + 0), b1 = __ldg(a.bg + 1), b2 = __ldg(a.bg + 2);
     *reinterpret_cast<float4*>(a.out_color + pid) =
         make_float4(__fmaf_rn(T[0], b0, Cr[0]), __fmaf_rn(T[1], b0, Cr[1]), __fmaf_rn(T[2], b0, Cr[2]),
@@ -252,7 +278,7 @@ __global__ void __launch_bounds__(R4_THREADS) k_render_fwd4(RenderArgs a) {
     for (int i = 0; i < 4; i++) {
       if (!t.in[i]) continue;
       a.pix[pid + i] = make_float4(Cr[i], Cg[i], Cb[i], T[i]);
-      a.n_contrib[pid + i] = last[i];
+      a.n_contrib[pid + i] = nstop[i];
       a.out_color[pid + i] = __fmaf_rn(T[i], __ldg(a.bg + 0), Cr[i]);
       a.out_color[hw + pid + i] = __fmaf_rn(T[i], __ldg(a.bg + 1), Cg[i]);
       a.out_color[2 * hw + pid + i] = __fmaf_rn(T[i], __ldg(a.bg + 2), Cb[i]);
@@ -293,7 +319,7 @@ __device__ __forceinline__ void r4_warp_reduce9(float (&v)[8], float& v8, int la
 //   dL/dalpha_j = T_j <c_j, g> - (F - R_j) / (1 - alpha_j),  F = <C_final, g> + T_final <bg, g>,
 //   R_j = sum_{k<=j} w_k <c_k, g>.
 // ==================================================================================================
-__global__ void __launch_bounds__(R4_THREADS) k_render_bwd4(RenderBwdArgs a) {
+__global__ void __launch_bounds__(R4_THREADS, R4_BWD_MINB) k_render_bwd4(RenderBwdArgs a) {
   __shared__ __align__(128) float4 sm[R4_STAGES][R4_CH * REC_F4];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
