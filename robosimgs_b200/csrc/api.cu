@@ -70,6 +70,20 @@ struct StageTimer {
 // keys), capped at 3 (64 compositing CTAs share one bin list).  B200GS_BIN_SHIFT overrides.
 static std::atomic<int> g_bin_shift_override{-2};   // -2: not initialised, -1: automatic
 
+// binning pipeline: 1 = bucketed (bucket.cu: per-bin counters + cursors, one per-bin sort launch;
+// default), 0 = global radix sort of (bin | depth) keys (binning.cu / coopsort.cu).
+// B200GS_BINNING=bucket|sort or b200gs_set_option("binning", 0|1).
+static std::atomic<int> g_binning_mode{-1};
+static bool use_bucketed() {
+  int m = g_binning_mode.load();
+  if (m < 0) {
+    const char* e = getenv("B200GS_BINNING");
+    m = (e && e[0] == 'b') ? 1 : 0;     // default: global sort (faster until the bucketed kernels are tuned)
+    g_binning_mode.store(m);
+  }
+  return m == 1;
+}
+
 static int bin_shift_for(int gx, int gy) {
   int forced = g_bin_shift_override.load();
   if (forced == -2) {
@@ -79,6 +93,13 @@ static int bin_shift_for(int gx, int gy) {
     g_bin_shift_override.store(forced);
   }
   if (forced >= 0) return forced;
+  if (use_bucketed()) {
+    // no key-width constraint: 64-px bins (shorter per-tile walks than 128 px, ~1.5x the pairs), coarser
+    // only to keep the single-CTA bin scan short on very large images
+    int s = 2;
+    while (s < 5 && (((gx + (1 << s) - 1) >> s) * ((gy + (1 << s) - 1) >> s)) > 8192) s++;
+    return s;
+  }
   int s = 0;
   while (s < 3 && (((gx + (1 << s) - 1) >> s) * ((gy + (1 << s) - 1) >> s)) > 255) s++;
   return s;
@@ -158,6 +179,9 @@ static ImgBuf carve_img(char* base, int H, int W, size_t* bytes) {
   im.ranges = c.take<uint2>(tiles);
   im.pix = c.take<float4>((size_t)H * W);
   im.n_contrib = c.take<uint32_t>((size_t)H * W);
+  im.bin_count = c.take<uint32_t>(tiles * BIN_STRIDE);
+  im.bin_cursor = c.take<uint32_t>(tiles * BIN_STRIDE);
+  im.bin_base = c.take<uint32_t>(tiles);
   if (bytes) *bytes = c.bytes();
   return im;
 }
@@ -243,6 +267,10 @@ int b200gs_set_option(const char* name, int value) {
   }
   if (name && !strcmp(name, "sort")) {
     g_sort_mode.store(value < 0 ? 1 : (value > 2 ? 2 : value));
+    return 0;
+  }
+  if (name && !strcmp(name, "binning")) {
+    g_binning_mode.store(value < 0 ? -1 : (value == 0 ? 0 : 1));   // -1: back to the default / environment
     return 0;
   }
   if (name && !strcmp(name, "render")) {
@@ -333,14 +361,36 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
   pa.view = viewmatrix; pa.proj = projmatrix; pa.campos = campos;
   pa.radii = radii; pa.rec = gb.rec; pa.depth_key = gb.depth_key; pa.tiles = gb.tiles;
   pa.clamped = gb.clamped;
+  const bool bucketed = use_bucketed();
+  pa.gbx = gbx;
+  pa.bin_count = bucketed ? ib.bin_count : nullptr;
+  if (bucketed && P > 0 &&
+      (rc = check_cuda(cudaMemsetAsync(ib.bin_count, 0, sizeof(uint32_t) * (size_t)num_tiles * BIN_STRIDE, st),
+                       "clear bin counters")))
+    return rc;
   {
     StageTimer t(0, st);
     launch_project(pa, shs ? prm->sh_degree : -1, st);
   }
   if ((rc = debug_sync(prm, st, "project"))) return rc;
+  // bucketed binning: D and the per-bin segment starts come from one scan of the bin counters
+  BucketArgs ba;
+  ba.P = P; ba.gx = gx; ba.gy = gy; ba.gbx = gbx; ba.bin_shift = bs;
+  ba.id_bits = 1;
+  while (ba.id_bits < 32 && (1ll << ba.id_bits) < (long long)P) ba.id_bits++;
+  ba.num_bins = (uint32_t)num_tiles; ba.capacity = 0xFFFFFFFFu;
+  ba.tiles = gb.tiles; ba.depth_key = gb.depth_key; ba.rec = gb.rec; ba.radii = radii;
+  ba.bin_count = ib.bin_count; ba.bin_cursor = ib.bin_cursor; ba.bin_base = ib.bin_base; ba.ranges = ib.ranges;
+  ba.total = gb.counters + 1; ba.big_queue = gb.big_queue; ba.big_count = gb.counters;
+  ba.seg = nullptr; ba.seg_alt = nullptr; ba.vals_sorted = nullptr;
+  const uint32_t* d_total = bucketed ? gb.counters + 1 : gb.offsets + (P > 0 ? P - 1 : 0);
   {
     StageTimer t(1, st);
-    if ((rc = scan_bin_counts(gb, P, st))) return rc;
+    if (!bucketed) {
+      if ((rc = scan_bin_counts(gb, P, st))) return rc;
+    } else if (P > 0) {
+      launch_bin_scan(ba, st);   // capacity unbounded: only D is consumed from this launch
+    }
   }
   if ((rc = debug_sync(prm, st, "scan"))) return rc;
 
@@ -354,7 +404,25 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
     int rc2;
     if ((rc2 = check_cuda(cudaMemsetAsync(ib.ranges, 0, sizeof(uint2) * (size_t)num_tiles, st), "clear ranges")))
       return rc2;
-    if (cap > 0) {
+    if (cap > 0 && bucketed) {
+      if ((rc2 = check_cuda(cudaMemsetAsync(gb.counters, 0, sizeof(uint32_t), st), "clear queue length"))) return rc2;
+      if ((rc2 = check_cuda(cudaMemsetAsync(ib.bin_cursor, 0, sizeof(uint32_t) * (size_t)num_tiles * BIN_STRIDE, st),
+                            "clear bin cursors")))
+        return rc2;
+      BucketArgs b2 = ba;
+      b2.capacity = cap; b2.seg = bb.keys; b2.seg_alt = bb.keys_sorted; b2.vals_sorted = bb.vals_sorted;
+      {
+        StageTimer t(2, st);
+        launch_bin_scan(b2, st);            // per-bin ranges clipped to this capacity
+        launch_bucket_emit_sort_emit(b2, st);
+      }
+      if ((rc2 = debug_sync(prm, st, "emit pairs"))) return rc2;
+      {
+        StageTimer t(3, st);
+        launch_bucket_emit_sort_sort(b2, st);
+      }
+      if ((rc2 = debug_sync(prm, st, "bin sort"))) return rc2;
+    } else if (cap > 0) {
       if ((rc2 = check_cuda(cudaMemsetAsync(gb.counters, 0, 32 * sizeof(uint32_t), st), "clear counters"))) return rc2;
       const int key_bits = 32 + tile_bits;
       const bool coop = use_coop_sort(cap);
@@ -417,7 +485,7 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
     if (!host_d) return B200GS_ERR_ALLOC;
     cudaEvent_t ev;
     if ((rc = check_cuda(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event create"))) return rc;
-    rc = check_cuda(cudaMemcpyAsync(host_d, gb.offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st),
+    rc = check_cuda(cudaMemcpyAsync(host_d, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st),
                     "queue num_rendered copy");
     if (!rc) rc = check_cuda(cudaEventRecord(ev, st), "event record");
     if (!rc) rc = run_binning_and_render((uint32_t)hint);
@@ -430,7 +498,7 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
     return 0;
   }
   if (P > 0) {
-    if ((rc = check_cuda(cudaMemcpyAsync(&D, gb.offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st),
+    if ((rc = check_cuda(cudaMemcpyAsync(&D, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st),
                          "read num_rendered")))
       return rc;
     if ((rc = check_cuda(cudaStreamSynchronize(st), "sync num_rendered"))) return rc;

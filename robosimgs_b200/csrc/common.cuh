@@ -60,7 +60,12 @@ struct BinBuf {
 struct ImgBuf {
   uint2* ranges;        // [tiles] [start,end) into the slab
   float4* pix;          // [H*W] {accumulated r,g,b (no background), final transmittance}
-  uint32_t* n_contrib;  // [H*W] 1-based list position of the last contributor
+  uint32_t* n_contrib;  // [H*W] list position behind which nothing contributes to the pixel
+  // bucketed binning (sized for the finest bins = 16-px tiles, so the layout never depends on the bin
+  // size): per-bin pair counters and append cursors, 256 B apart; per-bin segment starts
+  uint32_t* bin_count;  // [tiles * 64]
+  uint32_t* bin_cursor; // [tiles * 64]
+  uint32_t* bin_base;   // [tiles]
 };
 
 // ---- small math helpers ---------------------------------------------------------------------

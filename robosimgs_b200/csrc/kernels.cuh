@@ -4,8 +4,12 @@
 
 namespace b200gs {
 
+constexpr int BIN_STRIDE = 64;   // words between per-bin counters (256 B: one L2 atomic unit per bin)
+
 struct ProjectArgs {
   int P, M, W, H, gx, gy, sh_vec, bin_shift;
+  int gbx;               // bin grid width
+  uint32_t* bin_count;   // bucketed binning: per-bin pair counters (stride BIN_STRIDE), else nullptr
   float tanfovx, tanfovy, scale_modifier, near_plane;
   const float *means, *scales, *rots, *opac, *shs, *colors_precomp, *cov3d_precomp;
   const float *view, *proj, *campos;
@@ -27,6 +31,23 @@ struct EmitArgs {
   uint32_t* vals;       // Gaussian id
   uint32_t* big_queue;  // [P] ids of large-footprint Gaussians
   uint32_t* big_count;  // [1] zeroed before the emission stage
+};
+
+// bucketed binning (bucket.cu)
+struct BucketArgs {
+  int P, gx, gy, gbx, bin_shift;
+  int id_bits;              // bits of the largest Gaussian index
+  uint32_t num_bins, capacity;
+  const uint32_t *tiles, *depth_key;
+  const float4* rec;
+  const int32_t* radii;
+  uint32_t *bin_count, *bin_cursor;   // stride BIN_STRIDE
+  uint32_t* bin_base;                 // [num_bins]
+  uint2* ranges;                      // [num_bins] per-bin [start,end) into vals_sorted
+  uint32_t* total;                    // D
+  uint32_t *big_queue, *big_count;
+  uint64_t *seg, *seg_alt;            // [capacity] (depth bits << 32 | id), ping-pong
+  uint32_t* vals_sorted;              // [capacity] Gaussian ids in (bin, depth, index) order
 };
 
 struct RangesArgs {
@@ -107,6 +128,11 @@ void launch_photometric_loss(const float* a, const float* b, size_t n, float w_l
                              cudaStream_t st);
 void launch_photometric_loss_bwd(const float* a, const float* b, size_t n, float w_l2, float w_l1, float scale,
                                  const float* upstream, float* g, cudaStream_t st);
+
+// bucket.cu: bucketed binning (per-bin lists without a global sort)
+void launch_bin_scan(const BucketArgs& a, cudaStream_t st);
+void launch_bucket_emit_sort_emit(const BucketArgs& a, cudaStream_t st);
+void launch_bucket_emit_sort_sort(const BucketArgs& a, cudaStream_t st);
 
 // train.cu: fused SSIM and multi-tensor Adam
 void launch_ssim_fwd(const float* img1, const float* img2, int C, int H, int W, float* maps, float* out_sum,

@@ -241,8 +241,10 @@ def test_bin_shift_gather_and_sort_modes_never_change_results():
     w = torch.rand(3, 300, 400, generator=torch.Generator().manual_seed(17))
     base = None
     try:
-        for gather, sort in ((1, 2), (0, 2), (1, 0)):
-            for shift in (0, 1, 2, 3, 5):
+        # (binning, gather, sort): bucketed per-bin sort / global radix sort (cooperative, CUB)
+        for binning, gather, sort in ((1, 1, 1), (0, 1, 2), (0, 0, 2), (0, 1, 0)):
+            for shift in (-1, 0, 1, 2, 3, 5):
+                _cabi.set_option("binning", binning)
                 _cabi.set_option("gather", gather)
                 _cabi.set_option("sort", sort)
                 _cabi.set_option("bin_shift", shift)
@@ -250,13 +252,48 @@ def test_bin_shift_gather_and_sort_modes_never_change_results():
                 if base is None:
                     base = (color, radii, grads)
                     continue
-                assert np.array_equal(color, base[0]) and np.array_equal(radii, base[1]), (gather, sort, shift)
+                assert np.array_equal(color, base[0]) and np.array_equal(radii, base[1]), (binning, gather, sort, shift)
                 for k in ("means3D", "shs", "opacities", "scales", "rotations"):
-                    assert max_rel_err(grads[k], base[2][k]) < 1e-5, (gather, sort, shift, k)
+                    assert max_rel_err(grads[k], base[2][k]) < 1e-5, (binning, gather, sort, shift, k)
     finally:
+        _cabi.set_option("binning", -1)
         _cabi.set_option("gather", 1)
         _cabi.set_option("sort", 1)
         _cabi.set_option("bin_shift", -1)
+
+
+def test_equal_depths_keep_index_order_in_both_binning_pipelines():
+    """Depth ties must be composited in index order (a stable sort of index-ordered pairs).  A
+    fronto-parallel plane gives thousands of bit-identical view depths per bin (long runs: the bucketed
+    sort re-sorts the bin on the full key); a second scene quantises depth to a few values (short and
+    medium runs: insertion).  Both pipelines must agree bit for bit and match the oracle."""
+    from robosimgs_b200 import _cabi
+    from robosimgs_b200.cameras import camera_look_at
+    from robosimgs_b200.scenes import Scene, settings_from_camera
+    g = torch.Generator().manual_seed(41)
+    P = 6000
+    cam = camera_look_at((0.0, 0.0, 3.0), (0.0, 0.0, 0.0), (0, 1, 0), 50.0, 160, 120)
+    rs = settings_from_camera(cam, 0, bg=(0.1, 0.1, 0.1))
+    xy = torch.rand(P, 2, generator=g) * 2.4 - 1.2
+    rgb = torch.rand(P, 1, 3, generator=g)
+    common = dict(shs=(rgb - 0.5) / 0.28209479177387814, opacities=torch.rand(P, 1, generator=g) * 0.5 + 0.2,
+                  scales=torch.rand(P, 3, generator=g) * 0.05 + 0.02,
+                  rotations=torch.tensor([[1.0, 0, 0, 0]]).repeat(P, 1))
+    try:
+        for levels in (1, 700):
+            z = torch.zeros(P, 1) if levels == 1 else torch.randint(0, levels, (P, 1), generator=g).float() / 1024.0
+            sc = Scene(torch.cat([xy, z], 1), common["shs"], common["opacities"], common["scales"], common["rotations"], 0)
+            st = _oracle(rs, sc)
+            assert len(np.unique(st.depths[st.radii > 0])) <= levels
+            imgs = []
+            for binning in (1, 0):
+                _cabi.set_option("binning", binning)
+                color, radii, _ = gpu_render(sc, cam, 0, bg=(0.1, 0.1, 0.1))
+                assert psnr(color, st.color) >= PSNR_MIN, (levels, binning)
+                imgs.append(color)
+            assert np.array_equal(imgs[0], imgs[1]), levels
+    finally:
+        _cabi.set_option("binning", -1)
 
 
 def test_one_and_four_pixel_compositing_kernels_agree():
