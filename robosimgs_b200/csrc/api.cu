@@ -361,7 +361,7 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
   pa.view = viewmatrix; pa.proj = projmatrix; pa.campos = campos;
   pa.radii = radii; pa.rec = gb.rec; pa.depth_key = gb.depth_key; pa.tiles = gb.tiles;
   pa.clamped = gb.clamped;
-  const bool bucketed = use_bucketed();
+  const bool bucketed = use_bucketed() && num_tiles < 65535;   // staged bin ids are 16-bit (bucket.cu)
   pa.gbx = gbx;
   pa.bin_count = bucketed ? ib.bin_count : nullptr;
   if (bucketed && P > 0 &&
