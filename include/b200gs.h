@@ -46,6 +46,8 @@ extern "C" {
  * the device and are passed as pointers to b200gs_forward/backward, so a call never forces a
  * device->host copy of the camera.
  */
+#define B200GS_DEFER_PAIR_CHECK 1
+
 typedef struct B200GSParams {
   int32_t P;              /* number of Gaussians */
   int32_t sh_degree;      /* active SH degree, 0..3 */
@@ -58,7 +60,11 @@ typedef struct B200GSParams {
   int32_t prefiltered;    /* accepted for signature parity; culled Gaussians are simply skipped */
   int32_t debug;          /* !=0: synchronise and check for errors after every kernel */
   float near_plane;       /* near cull on view-space z; <= 0 selects the public default 0.2 */
-  int32_t reserved0;
+  int32_t flags;          /* bit 0 (B200GS_DEFER_PAIR_CHECK): with pair_capacity_hint > 0, do not wait for D at
+                             all -- *num_rendered must then point to PINNED host memory, receives D
+                             asynchronously on `stream`, and the CALLER checks D <= pair_capacity_hint once the
+                             stream has passed the call (a frame that fails the check is incomplete and must be
+                             rendered again).  Lets a sweep keep many independent frames in flight. */
   int64_t pair_capacity_hint; /* 0: size the binning buffer exactly (host waits for D before
                                  launching the binning stage, as the replaced interface does).
                                  >0: launch the whole frame for this many (Gaussian,tile) pair

@@ -20,6 +20,7 @@ EXPORTED_SYMBOLS = (
     "b200gs_ssim_forward", "b200gs_ssim_backward", "b200gs_adam_step",
 )
 ADAM_MAX_GROUPS = 8
+DEFER_PAIR_CHECK = 1
 NUM_STAGES = 8
 
 
@@ -28,7 +29,7 @@ class B200GSParams(C.Structure):
         ("P", C.c_int32), ("sh_degree", C.c_int32), ("M", C.c_int32),
         ("image_height", C.c_int32), ("image_width", C.c_int32),
         ("tanfovx", C.c_float), ("tanfovy", C.c_float), ("scale_modifier", C.c_float),
-        ("prefiltered", C.c_int32), ("debug", C.c_int32), ("near_plane", C.c_float), ("reserved0", C.c_int32),
+        ("prefiltered", C.c_int32), ("debug", C.c_int32), ("near_plane", C.c_float), ("flags", C.c_int32),
         ("pair_capacity_hint", C.c_int64),
     ]
 
@@ -72,7 +73,7 @@ def lib():
     L.b200gs_forward.restype = C.c_int
     L.b200gs_forward.argtypes = [C.POINTER(B200GSParams), fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, fp,
                                  fp, vp, B200GSAlloc, B200GSAlloc, B200GSAlloc,
-                                 C.POINTER(C.c_int32), vp]
+                                 vp, vp]      # num_rendered: int32* (pinned host memory in deferred mode)
     L.b200gs_backward.restype = C.c_int
     L.b200gs_backward.argtypes = [C.POINTER(B200GSParams), fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, fp,
                                   vp, vp, vp, vp, C.c_int32, fp,

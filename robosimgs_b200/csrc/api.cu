@@ -477,6 +477,13 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
 
   uint32_t D = 0;
   const int64_t hint = prm->pair_capacity_hint;
+  if (P > 0 && hint > 0 && hint < (int64_t)0x7fffffff && (prm->flags & B200GS_DEFER_PAIR_CHECK)) {
+    // Deferred check: D goes straight to the caller's pinned word; the host never waits here.
+    if ((rc = check_cuda(cudaMemcpyAsync(num_rendered, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st),
+                         "queue num_rendered copy (deferred)")))
+      return rc;
+    return run_binning_and_render((uint32_t)hint);
+  }
   if (P > 0 && hint > 0 && hint < (int64_t)0x7fffffff) {
     // Speculative path: D stays on the device.  Its copy to pinned host memory is queued, the rest
     // of the frame is launched for `hint` pair slots, and only then does the host wait for the copy

@@ -147,16 +147,46 @@ _PAIR_HINTS: dict = {}
 SPECULATE_PAIR_CAPACITY = True
 
 
-def _params(P, M, rs: GaussianRasterizationSettings, hint: int = 0, near_plane: float = 0.0) -> _cabi.B200GSParams:
+def _params(P, M, rs: GaussianRasterizationSettings, hint: int = 0, near_plane: float = 0.0,
+            flags: int = 0) -> _cabi.B200GSParams:
     return _cabi.B200GSParams(int(P), int(rs.sh_degree), int(M), int(rs.image_height), int(rs.image_width),
                               float(rs.tanfovx), float(rs.tanfovy), float(rs.scale_modifier),
-                              int(bool(rs.prefiltered)), int(bool(rs.debug)), float(near_plane), 0, int(hint))
+                              int(bool(rs.prefiltered)), int(bool(rs.debug)), float(near_plane), int(flags), int(hint))
+
+
+class PairTicket:
+    """Receipt of a forward call made with the pair-count check DEFERRED (forward-only sweeps).
+
+    The library launched the frame for `hint` pair slots and returned without waiting for the pair
+    count D; D arrives in a pinned word once the frame's stream has passed the call.  ``ok()`` waits
+    for that point and tells whether the frame is complete (D <= hint).  A frame that is not must be
+    rendered again (``GaussianRasterizer.forward`` does it exactly) -- with the decaying-maximum hints
+    this happens only on abrupt view changes."""
+    _free_words: list = []
+
+    def __init__(self, hint: int, hint_key):
+        self.hint, self.hint_key = int(hint), hint_key
+        self.word = PairTicket._free_words.pop() if PairTicket._free_words else torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.event = None
+        self._ok = None
+
+    def ok(self) -> bool:
+        if self._ok is None:
+            if self.event is not None:
+                self.event.synchronize()
+            D = int(self.word[0])
+            self._ok = self.hint <= 0 or D <= self.hint
+            last = _PAIR_HINTS.get(self.hint_key, 0)
+            _PAIR_HINTS[self.hint_key] = max(D, int(last * 0.97))
+            PairTicket._free_words.append(self.word)
+            self.word = None
+        return self._ok
 
 
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
-                cov3Ds_precomp, raster_settings, grad_mode=True, near_plane=0.0, want_alpha=False):
+                cov3Ds_precomp, raster_settings, grad_mode=True, near_plane=0.0, want_alpha=False, ticket_box=None):
         L = _cabi.lib()
         rs = raster_settings
         if getattr(rs, "antialiasing", False):
@@ -181,10 +211,20 @@ class _RasterizeGaussians(torch.autograd.Function):
         H, W = int(rs.image_height), int(rs.image_width)
         hint_key = (dev.index, P, H, W)
         last_D = _PAIR_HINTS.get(hint_key, 0) if SPECULATE_PAIR_CAPACITY and not rs.debug else 0
-        prm = _params(P, M, rs, last_D + (last_D >> 4) + 32768 if last_D > 0 else 0, near_plane)
+        hint = last_D + (last_D >> 4) + 32768 if last_D > 0 else 0
+        # deferred pair check (forward-only callers that pass a ticket box): only once a hint exists
+        ticket = None
+        if ticket_box is not None:
+            if grad_mode and any(ctx.needs_input_grad):
+                raise _cabi.B200GSError("the deferred pair check is for forward-only rendering (no_grad)")
+            ticket = PairTicket(hint if P > 0 else 0, hint_key)
+            ticket_box.append(ticket)
+        defer = ticket is not None and hint > 0 and P > 0
+        prm = _params(P, M, rs, hint, near_plane, _cabi.DEFER_PAIR_CHECK if defer else 0)
         color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
         radii = torch.empty((P,), dtype=torch.int32, device=dev)
         num_rendered = C.c_int32(0)
+        nr_ptr = C.c_void_p(ticket.word.data_ptr()) if defer else C.cast(C.pointer(num_rendered), C.c_void_p)
         with torch.cuda.device(dev):
             lease = _Lease(dev, ("geom", "binning", "img"))
             stream = C.c_void_p(lease.stream)
@@ -192,7 +232,13 @@ class _RasterizeGaussians(torch.autograd.Function):
                 C.byref(prm), _ptr(bg), _ptr(view), _ptr(proj), _ptr(campos), _ptr(means3D), _ptr(sh),
                 _ptr(colors_precomp), _ptr(opacities), _ptr(scales), _ptr(rotations),
                 _ptr(cov3Ds_precomp), _ptr(color), _ptr(radii), lease.allocs["geom"], lease.allocs["binning"],
-                lease.allocs["img"], C.byref(num_rendered), stream))
+                lease.allocs["img"], nr_ptr, stream))
+            if defer:
+                ticket.event = torch.cuda.Event()
+                ticket.event.record(torch.cuda.current_stream(dev))
+            elif ticket is not None:
+                ticket.word[0] = int(num_rendered.value)     # synchronous path: already exact
+                ticket.hint = 0
             alpha = None
             if want_alpha:
                 alpha = torch.empty((H, W), dtype=torch.float32, device=dev)
@@ -201,7 +247,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.raster_settings = rs
         ctx.near_plane = near_plane
         ctx.num_rendered = int(num_rendered.value)
-        _PAIR_HINTS[hint_key] = max(ctx.num_rendered, int(last_D * 0.97))
+        if not defer:
+            _PAIR_HINTS[hint_key] = max(ctx.num_rendered, int(last_D * 0.97))
         ctx.M = M
         ctx.present = (sh is not None, colors_precomp is not None, scales is not None,
                        cov3Ds_precomp is not None)
@@ -256,7 +303,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             lease.release()
         # order of the public interface: means3D, means2D, sh, colors_precomp, opacities, scales,
         # rotations, cov3Ds_precomp, raster_settings
-        return g_means3D, g_means2D, g_sh, g_col, g_opac, g_scales, g_rots, g_cov, None, None, None, None
+        return g_means3D, g_means2D, g_sh, g_col, g_opac, g_scales, g_rots, g_cov, None, None, None, None, None
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
@@ -287,6 +334,24 @@ class GaussianRasterizer(nn.Module):
                 _cabi.check(L.b200gs_mark_visible(C.c_int32(pos.shape[0]), _ptr(pos), _ptr(view), _ptr(proj),
                                                   _ptr(out), stream))
         return out.bool()
+
+    def forward_deferred(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None,
+                         rotations=None, cov3D_precomp=None):
+        """Forward-only render that never blocks the host: returns ``(color, radii, ticket)``.  The frame
+        may be consumed once ``ticket.ok()`` is True; if it is False (pair count above the speculative
+        capacity) call ``forward`` again for this frame.  Use under ``torch.no_grad()``."""
+        if (shs is None) == (colors_precomp is None):
+            raise Exception("Please provide excatly one of either SHs or precomputed colors!")
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
+        e = means3D.new_empty(0)
+        box = []
+        color, radii = _RasterizeGaussians.apply(
+            means3D, means2D, e if shs is None else shs, e if colors_precomp is None else colors_precomp, opacities,
+            e if scales is None else scales, e if rotations is None else rotations,
+            e if cov3D_precomp is None else cov3D_precomp, self.raster_settings, False, 0.0, False, box)
+        return color, radii, box[0]
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None,
                 rotations=None, cov3D_precomp=None):

@@ -40,20 +40,27 @@ def replicate_scene(tensors: Optional[dict], device, src: int = 0) -> dict:
     return out
 
 
-def default_render_fn(scene: dict, sh_degree: int, bg: torch.Tensor) -> Callable[[Camera], torch.Tensor]:
+def default_render_fn(scene: dict, sh_degree: int, bg: torch.Tensor, deferred: bool = False):
+    """cam -> frame.  With deferred=True: cam -> (frame, ticket) through GaussianRasterizer.forward_deferred
+    (the host never waits for the frame's pair count; render_sweep validates the ticket later)."""
     from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer
     dev = scene["means3D"].device
     means2D = torch.zeros_like(scene["means3D"])
 
-    def render(cam: Camera) -> torch.Tensor:
+    def render(cam: Camera, force_exact: bool = False):
         rs = GaussianRasterizationSettings(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy, bg, 1.0,
                                            cam.viewmatrix.to(dev, non_blocking=True),
                                            cam.projmatrix.to(dev, non_blocking=True), sh_degree,
                                            cam.campos.to(dev, non_blocking=True), False, False)
         with torch.no_grad():
-            color, _ = GaussianRasterizer(rs)(scene["means3D"], means2D, scene["opacities"], shs=scene["shs"],
-                                              scales=scene["scales"], rotations=scene["rotations"])
-        return color
+            r = GaussianRasterizer(rs)
+            kw = dict(shs=scene["shs"], scales=scene["scales"], rotations=scene["rotations"])
+            if deferred and not force_exact:
+                color, _, ticket = r.forward_deferred(scene["means3D"], means2D, scene["opacities"], **kw)
+                return color, ticket
+            color, _ = r(scene["means3D"], means2D, scene["opacities"], **kw)
+        return (color, None) if deferred else color
+    render.deferred = deferred
     return render
 
 
@@ -106,16 +113,33 @@ def render_sweep(cameras: Sequence[Camera], render_fn: Callable[[Camera], torch.
         dev = torch.device("cuda", torch.cuda.current_device())
         fs = FrameStreams(dev, streams)
         fs.fork()
-        dmeans = []
-        for f in mine:
-            with fs.next():
-                frame = render_fn(cameras[f])
+        deferred = bool(getattr(render_fn, "deferred", False))
+        dmeans, pending = {}, []
+
+        def finish(entry):
+            # runs with the frame's stream current; a frame whose speculative pair capacity was too small
+            # (ticket not ok -- abrupt view change) is rendered again, exactly
+            f, frame, ticket, stream = entry
+            with torch.cuda.stream(stream):
+                if ticket is not None and not ticket.ok():
+                    frame, _ = render_fn(cameras[f], force_exact=True)
                 if on_frame is not None:
                     on_frame(f, frame)
-                dmeans.append(frame.mean(dtype=torch.float64))      # stays on the device: no per-frame sync
+                dmeans[f] = frame.mean(dtype=torch.float64)          # stays on the device: no per-frame sync
+
+        for f in mine:
+            ctx = fs.next()
+            with ctx:
+                out = render_fn(cameras[f])
+                frame, ticket = out if deferred else (out, None)
+                pending.append((f, frame, ticket, torch.cuda.current_stream(dev)))
+            if len(pending) > 2 * streams:       # validate with a lag, so the host never waits on a fresh frame
+                finish(pending.pop(0))
+        while pending:
+            finish(pending.pop(0))
         fs.join()
         if mine:
-            means[torch.tensor(mine)] = torch.stack(dmeans).cpu()
+            means[torch.tensor(mine)] = torch.stack([dmeans[f] for f in mine]).cpu()
     else:
         for f in mine:
             frame = render_fn(cameras[f])
@@ -148,8 +172,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     sc, cams = sweep_scene(a.gaussians, a.cameras)
     scene = replicate_scene({k: getattr(sc, k) for k in SCENE_FIELDS} if rank == 0 else None, dev)
-    render = default_render_fn(scene, sc.sh_degree, torch.zeros(3, device=dev))
-    render(cams[rank % len(cams)])
+    render = default_render_fn(scene, sc.sh_degree, torch.zeros(3, device=dev), deferred=True)
+    render(cams[rank % len(cams)], force_exact=True)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

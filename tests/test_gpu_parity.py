@@ -221,6 +221,42 @@ def test_speculative_pair_capacity_paths_are_bit_identical():
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][0], outs[2][0])
 
 
+def test_deferred_pair_check_ticket_protocol():
+    """forward_deferred never blocks on the pair count: same image as forward when the hint suffices
+    (ticket ok), ticket not ok when the speculative capacity was too small (caller renders again)."""
+    from robosimgs_b200 import GaussianRasterizer, _cabi, rasterizer
+    from robosimgs_b200.scenes import settings_from_camera
+    dev = torch.device("cuda:0")
+    sc, cam, _ = small_scene(P=30000, degree=1, W=400, H=300)
+    rs = settings_from_camera(cam, 1, bg=(0.2, 0.1, 0.4), device=dev)
+    t = {k: getattr(sc, k).to(dev) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+    m2 = torch.zeros_like(t["means3D"])
+    kw = dict(shs=t["shs"], scales=t["scales"], rotations=t["rotations"])
+    try:
+        _cabi.set_option("bin_shift", 0)
+        with torch.no_grad():
+            r = GaussianRasterizer(rs)
+            rasterizer._PAIR_HINTS.clear()
+            c0, r0, t0 = r.forward_deferred(t["means3D"], m2, t["opacities"], **kw)     # no hint yet: exact path
+            assert t0.ok()
+            ref, rref = r(t["means3D"], m2, t["opacities"], **kw)
+            assert torch.equal(c0, ref)
+            c1, r1, t1 = r.forward_deferred(t["means3D"], m2, t["opacities"], **kw)     # hint from the last frames
+            assert t1.hint > 0 and t1.ok()
+            assert torch.equal(c1, ref) and torch.equal(r1, rref)
+            key = t1.hint_key
+            D = rasterizer._PAIR_HINTS[key]
+            assert D > 40000, D                                     # above the 32768 slots of head-room
+            rasterizer._PAIR_HINTS[key] = 16                        # a stale, far too small hint
+            c2, _, t2 = r.forward_deferred(t["means3D"], m2, t["opacities"], **kw)
+            assert not t2.ok()                                      # incomplete frame: must be rendered again
+            assert rasterizer._PAIR_HINTS[key] >= D                 # ... and the hint has recovered
+            c3, _, t3 = r.forward_deferred(t["means3D"], m2, t["opacities"], **kw)
+            assert t3.ok() and torch.equal(c3, ref)
+    finally:
+        _cabi.set_option("bin_shift", -1)
+
+
 def test_export_rgb8_matches_numpy():
     from robosimgs_b200 import export_rgb8
     g = torch.Generator().manual_seed(5)
