@@ -342,70 +342,34 @@ def run_b200(args):
     clocks = sampler.stop()
     del leaves, m2
 
-    # ---- e2e: camera from pinned host memory each frame, finished frame back to pinned host memory ----
-    host_cams = []
-    for c in cams:
-        pack = torch.cat([c.viewmatrix.reshape(-1), c.projmatrix.reshape(-1), c.campos.reshape(-1)]).pin_memory()
-        host_cams.append((c, pack))
+    # ---- e2e: HOST buffers on both sides through the public per-frame renderer (sweep.SceneRenderer):
+    # camera block from pinned host memory in, finished 8-bit frame in pinned host memory out, every
+    # frame collected (and its pair-count ticket validated) by the consumer inside the timed region ----
+    from robosimgs_b200.sweep import SceneRenderer
     NS = max(1, args.e2e_streams)
-    NBUF = 2 * NS
-    host_frames = [torch.empty((H_IMG, W_IMG, 3), dtype=torch.uint8).pin_memory() for _ in range(NBUF)]
-    h2d_bytes = host_cams[0][1].numel() * 4
-    d2h_bytes = host_frames[0].numel()
-    frame_done = [torch.cuda.Event() for _ in range(NBUF)]
-    fs_e2e = FrameStreams(dev, NS)
-
-    e2e_tickets = [None] * NBUF
-    e2e_redone = [0]
-
-    def e2e_frame(s, exact=False):
-        c, pack = host_cams[(Wm + s) % nframes]
-        d = pack.to(dev, non_blocking=True)
-        rs = GaussianRasterizationSettings(c.image_height, c.image_width, c.tanfovx, c.tanfovy, bg, 1.0,
-                                           d[0:16].view(4, 4), d[16:32].view(4, 4), SH_DEG, d[32:35], False, False)
-        ticket = None
-        if exact:
-            col, _ = render(rs)
-        else:
-            col, _, ticket = GaussianRasterizer(rs).forward_deferred(
-                tens["means3D"], means2D, tens["opacities"], shs=tens["shs"], scales=tens["scales"],
-                rotations=tens["rotations"])
-        col = export_rgb8(col)      # 8-bit HWC frame, the format the datagen sweep stores
-        host_frames[s % NBUF].copy_(col, non_blocking=True)
-        frame_done[s % NBUF].record()
-        return ticket
-
-    def consume(s):
-        # consumer side: the frame is on the host; a frame whose speculative pair capacity was too small is redone
-        ticket, stream = e2e_tickets[s % NBUF]
-        frame_done[s % NBUF].synchronize()
-        if ticket is not None and not ticket.ok():
-            e2e_redone[0] += 1
-            with torch.cuda.stream(stream):
-                e2e_frame(s, exact=True)
-            frame_done[s % NBUF].synchronize()
+    renderer = SceneRenderer(tens, SH_DEG, bg, H_IMG, W_IMG, streams=NS, graphs=not args.no_graphs)
+    h2d_bytes = 35 * 4
+    d2h_bytes = H_IMG * W_IMG * 3
+    handles = []
+    last_frame = [None]
 
     def e2e_step(s):
-        # frame s: camera H2D, render, 8-bit export and the D2H read of the finished frame are all queued
-        # on the frame's stream without any host wait; with several streams one frame's copy-out overlaps
-        # the others' render.  Frames are consumed (and validated) NS frames later.
-        with fs_e2e.next():
-            e2e_tickets[s % NBUF] = (e2e_frame(s), torch.cuda.current_stream(dev))
-        if s >= NS:
-            consume(s - NS)
+        while len(handles) >= renderer.in_flight_limit():
+            last_frame[0] = renderer.collect(handles.pop(0))
+        handles.append(renderer.submit(cams[(Wm + s) % nframes]))
         if s == K - 1:
-            for t in range(max(0, K - NS), K):     # the last frames are consumed inside the timed region
-                consume(t)
+            while handles:                      # the last frames are collected inside the timed region
+                last_frame[0] = renderer.collect(handles.pop(0))
 
-    with torch.no_grad():
-        for s in range(max(Wm, 3) + 2):
-            with fs_e2e.next():
-                e2e_frame(s, exact=True)
-        fs_e2e.join()
-        torch.cuda.synchronize()
-        fs_e2e.i = 0
-        e2e_ms = timed(e2e_step, K, fs_e2e)
-    checksum = float(host_frames[(K - 1) % NBUF].double().mean())
+    for s in range(max(Wm, 3) + 2 * renderer.in_flight_limit()):      # warm-up: exact frame, then graph capture per slot
+        e2e_step(s)
+    while handles:
+        renderer.collect(handles.pop(0))
+    torch.cuda.synchronize()
+    renderer.redone = 0
+    e2e_ms = timed(e2e_step, K, renderer.fs)
+    checksum = float(last_frame[0].double().mean())
+    e2e_redone = [renderer.redone]
 
     if rank != 0:
         if world > 1:
@@ -451,10 +415,11 @@ def run_b200(args):
         "e2e": {"value": e2e_val, "unit": "Mpixels/s", "ms_per_step": e2e_ms / K,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "frames_rendered_twice": e2e_redone[0], "streams": NS,
-                "what": "GaussianRasterizer.forward_deferred + export_rgb8 per frame: camera (view, proj, campos) from pinned "
-                        "host memory, finished 8-bit RGB frame copied to pinned host memory, all on the frame's "
-                        "stream (consecutive frames alternate streams); scene resident in HBM as in the reference's "
-                        "render loop"},
+                "cuda_graphs": not args.no_graphs,
+                "what": "robosimgs_b200.sweep.SceneRenderer.submit/collect per frame: camera (view, proj, campos) from "
+                        "pinned host memory, forward with deferred pair check + export_rgb8, finished 8-bit RGB frame "
+                        "copied to pinned host memory and collected by the consumer; one captured CUDA graph per frame "
+                        "slot, consecutive frames alternate streams; scene resident in HBM as in the reference's render loop"},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": dom_gbs, "peak": peak, "unit": "GB/s",
                      "frac": dom_gbs / peak, "traffic": traffic, "peak_source": peak_src,
@@ -505,8 +470,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=3, help="CUDA streams the frames of the sweep alternate over")
-    ap.add_argument("--e2e-streams", type=int, default=2, help="same, for the end-to-end (host buffers) measurement")
+    ap.add_argument("--streams", type=int, default=4, help="CUDA streams the frames of the sweep alternate over")
+    ap.add_argument("--e2e-streams", type=int, default=4, help="same, for the end-to-end (host buffers) measurement")
+    ap.add_argument("--no-graphs", action="store_true", help="end-to-end path without CUDA graphs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

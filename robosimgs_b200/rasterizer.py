@@ -95,6 +95,7 @@ class _ScratchPool:
 
 
 _POOL = _ScratchPool()
+LEASE_TAG = None
 
 
 class _Lease:
@@ -107,7 +108,9 @@ class _Lease:
         self.device = device
         self.stream = torch.cuda.current_stream(device).cuda_stream
         self.tensors = tensors = {}
-        keys = {k: (device.index, self.stream, k) for k in kinds}
+        # LEASE_TAG (set by sweep.SceneRenderer) gives a caller private scratch: buffers used inside a
+        # captured CUDA graph must never be handed to eager calls on the same stream
+        keys = {k: (device.index, self.stream, k, LEASE_TAG) for k in kinds}
         self._keys = keys
 
         def make(kind):
@@ -164,23 +167,40 @@ class PairTicket:
     this happens only on abrupt view changes."""
     _free_words: list = []
 
-    def __init__(self, hint: int, hint_key):
+    def __init__(self, hint: int, hint_key, word=None):
         self.hint, self.hint_key = int(hint), hint_key
-        self.word = PairTicket._free_words.pop() if PairTicket._free_words else torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._own_word = word is None
+        if word is None:
+            word = PairTicket._free_words.pop() if PairTicket._free_words else torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.word = word
         self.event = None
         self._ok = None
+        self.pairs = None
 
     def ok(self) -> bool:
         if self._ok is None:
             if self.event is not None:
                 self.event.synchronize()
-            D = int(self.word[0])
+            D = self.pairs = int(self.word[0])
             self._ok = self.hint <= 0 or D <= self.hint
             last = _PAIR_HINTS.get(self.hint_key, 0)
             _PAIR_HINTS[self.hint_key] = max(D, int(last * 0.97))
-            PairTicket._free_words.append(self.word)
+            if self._own_word:
+                PairTicket._free_words.append(self.word)
             self.word = None
         return self._ok
+
+
+class DeferOptions(list):
+    """Ticket box of a deferred forward call (the ticket is appended) with optional overrides:
+    capacity -- explicit pair capacity instead of the decaying-maximum hint (a captured CUDA graph
+    needs launch arguments that do not change from frame to frame); word -- caller-owned pinned int32
+    word that receives the pair count; record_event -- False inside stream capture (the caller records
+    its own event after replaying the graph)."""
+
+    def __init__(self, capacity: int = 0, word=None, record_event: bool = True):
+        super().__init__()
+        self.capacity, self.word, self.record_event = int(capacity), word, bool(record_event)
 
 
 class _RasterizeGaussians(torch.autograd.Function):
@@ -217,7 +237,10 @@ class _RasterizeGaussians(torch.autograd.Function):
         if ticket_box is not None:
             if grad_mode and any(ctx.needs_input_grad):
                 raise _cabi.B200GSError("the deferred pair check is for forward-only rendering (no_grad)")
-            ticket = PairTicket(hint if P > 0 else 0, hint_key)
+            opts = ticket_box if isinstance(ticket_box, DeferOptions) else DeferOptions()
+            if opts.capacity > 0:
+                hint = opts.capacity
+            ticket = PairTicket(hint if P > 0 else 0, hint_key, opts.word)
             ticket_box.append(ticket)
         defer = ticket is not None and hint > 0 and P > 0
         prm = _params(P, M, rs, hint, near_plane, _cabi.DEFER_PAIR_CHECK if defer else 0)
@@ -234,8 +257,9 @@ class _RasterizeGaussians(torch.autograd.Function):
                 _ptr(cov3Ds_precomp), _ptr(color), _ptr(radii), lease.allocs["geom"], lease.allocs["binning"],
                 lease.allocs["img"], nr_ptr, stream))
             if defer:
-                ticket.event = torch.cuda.Event()
-                ticket.event.record(torch.cuda.current_stream(dev))
+                if opts.record_event:
+                    ticket.event = torch.cuda.Event()
+                    ticket.event.record(torch.cuda.current_stream(dev))
             elif ticket is not None:
                 ticket.word[0] = int(num_rendered.value)     # synchronous path: already exact
                 ticket.hint = 0
@@ -336,7 +360,7 @@ class GaussianRasterizer(nn.Module):
         return out.bool()
 
     def forward_deferred(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None,
-                         rotations=None, cov3D_precomp=None):
+                         rotations=None, cov3D_precomp=None, options: Optional[DeferOptions] = None):
         """Forward-only render that never blocks the host: returns ``(color, radii, ticket)``.  The frame
         may be consumed once ``ticket.ok()`` is True; if it is False (pair count above the speculative
         capacity) call ``forward`` again for this frame.  Use under ``torch.no_grad()``."""
@@ -346,12 +370,12 @@ class GaussianRasterizer(nn.Module):
                 ((scales is not None or rotations is not None) and cov3D_precomp is not None):
             raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
         e = means3D.new_empty(0)
-        box = []
+        box = options if options is not None else DeferOptions()
         color, radii = _RasterizeGaussians.apply(
             means3D, means2D, e if shs is None else shs, e if colors_precomp is None else colors_precomp, opacities,
             e if scales is None else scales, e if rotations is None else rotations,
             e if cov3D_precomp is None else cov3D_precomp, self.raster_settings, False, 0.0, False, box)
-        return color, radii, box[0]
+        return color, radii, box[-1]
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None,
                 rotations=None, cov3D_precomp=None):

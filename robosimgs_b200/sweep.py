@@ -96,6 +96,133 @@ class FrameStreams:
             main.wait_stream(s)
 
 
+class SceneRenderer:
+    """Per-frame scene render with HOST buffers on both sides -- the datagen loop of the reference's
+    (unreleased) renderer, /root/reference/README.md:29,85: camera in (host), 8-bit frame out (host).
+
+    The scene stays resident in HBM.  A ring of `2 * streams` frame slots alternates over `streams` CUDA
+    streams; every slot owns a pinned camera block, a pinned frame, private scratch and -- with
+    graphs=True -- ONE captured CUDA graph of the whole frame (camera H2D, the ~18 launches of the
+    rasterizer's forward with the pair-count check deferred, RGB8 export, frame D2H), so submitting a
+    frame costs the host one graph launch instead of ~25 API calls.  The graph is captured for a fixed
+    pair capacity (quantised, with head-room); a frame whose pair count exceeds it is detected when it
+    is collected (PairTicket) and rendered again exactly, and the graphs are re-captured for the larger
+    capacity.
+
+        r = SceneRenderer(scene, sh_degree, bg, H, W)
+        h = r.submit(cam)          # returns at once
+        frame = r.collect(h)       # uint8 [H, W, 3] pinned host tensor, valid until the slot is reused
+    """
+
+    _tags = 0
+
+    def __init__(self, scene: dict, sh_degree: int, bg: torch.Tensor, height: int, width: int, streams: int = 2,
+                 graphs: bool = True):
+        from . import rasterizer
+        self.rz = rasterizer
+        self.scene, self.deg, self.H, self.W = scene, int(sh_degree), int(height), int(width)
+        self.dev = scene["means3D"].device
+        self.bg = bg.to(self.dev)
+        self.means2D = torch.zeros_like(scene["means3D"])
+        self.graphs = bool(graphs)
+        self.capacity = 0
+        self.redone = 0
+        self.fs = FrameStreams(self.dev, streams)
+        self.slots = []
+        for i in range(2 * len(self.fs.streams)):
+            SceneRenderer._tags += 1
+            self.slots.append(dict(
+                stream=self.fs.streams[i % len(self.fs.streams)], tag=("scene-renderer", SceneRenderer._tags),
+                cam_host=torch.zeros(35, dtype=torch.float32).pin_memory(), cam_dev=torch.zeros(35, device=self.dev),
+                frame_host=torch.empty((self.H, self.W, 3), dtype=torch.uint8).pin_memory(),
+                rgb8=torch.empty((self.H, self.W, 3), dtype=torch.uint8, device=self.dev),
+                word=torch.zeros(1, dtype=torch.int32).pin_memory(), event=torch.cuda.Event(),
+                graph=None, graph_capacity=0, ticket=None, busy=False, cam=None))
+        self.n = 0
+
+    # -- one frame on the current stream -------------------------------------------------------------
+    def _enqueue(self, slot, tanfovx, tanfovy, exact: bool, in_capture: bool):
+        rz = self.rz
+        d = slot["cam_dev"]
+        d.copy_(slot["cam_host"], non_blocking=True)
+        rs = rz.GaussianRasterizationSettings(self.H, self.W, tanfovx, tanfovy, self.bg, 1.0, d[0:16].view(4, 4),
+                                              d[16:32].view(4, 4), self.deg, d[32:35], False, False)
+        sc = self.scene
+        kw = dict(shs=sc["shs"], scales=sc["scales"], rotations=sc["rotations"])
+        r = rz.GaussianRasterizer(rs)
+        ticket = None
+        rz.LEASE_TAG = slot["tag"]
+        try:
+            if exact or self.capacity <= 0:
+                color, _ = r(sc["means3D"], self.means2D, sc["opacities"], **kw)
+            else:
+                opts = rz.DeferOptions(capacity=self.capacity, word=slot["word"], record_event=False)
+                color, _, ticket = r.forward_deferred(sc["means3D"], self.means2D, sc["opacities"], options=opts, **kw)
+            rz.export_rgb8(color, out=slot["rgb8"])
+        finally:
+            rz.LEASE_TAG = None
+        slot["frame_host"].copy_(slot["rgb8"], non_blocking=True)
+        return ticket
+
+    def _set_capacity(self, pairs: int) -> None:
+        q = 1 << 16
+        self.capacity = ((int(pairs * 1.0625) + 32768 + q - 1) // q) * q
+
+    def submit(self, cam: Camera) -> int:
+        slot = self.slots[self.n % len(self.slots)]
+        if slot["busy"]:
+            raise RuntimeError("SceneRenderer: collect() the oldest frame before submitting more "
+                               f"({len(self.slots)} frames may be in flight)")
+        handle = self.n
+        self.n += 1
+        h = slot["cam_host"]
+        h[0:16] = cam.viewmatrix.reshape(-1)
+        h[16:32] = cam.projmatrix.reshape(-1)
+        h[32:35] = cam.campos.reshape(-1)
+        slot["cam"], slot["busy"] = cam, True
+        tf = (float(cam.tanfovx), float(cam.tanfovy))
+        with torch.no_grad(), torch.cuda.stream(slot["stream"]):
+            if self.capacity <= 0:                       # first frame: exact path, learn the pair count
+                self._enqueue(slot, *tf, exact=True, in_capture=False)
+                slot["ticket"] = None
+                key = (self.dev.index, self.scene["means3D"].shape[0], self.H, self.W)
+                self._set_capacity(self.rz._PAIR_HINTS.get(key, 0))
+            elif self.graphs:
+                if slot["graph"] is None or slot["graph_capacity"] != self.capacity or slot.get("tf") != tf:
+                    self._enqueue(slot, *tf, exact=False, in_capture=False)       # sizes this slot's private scratch
+                    slot["stream"].synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=slot["stream"]):
+                        self._enqueue(slot, *tf, exact=False, in_capture=True)
+                    slot["graph"], slot["graph_capacity"], slot["tf"] = g, self.capacity, tf
+                slot["graph"].replay()
+                key = (self.dev.index, self.scene["means3D"].shape[0], self.H, self.W)
+                slot["ticket"] = self.rz.PairTicket(self.capacity, key, slot["word"])
+            else:
+                slot["ticket"] = self._enqueue(slot, *tf, exact=False, in_capture=False)
+            slot["event"].record(slot["stream"])
+        return handle
+
+    def collect(self, handle: int) -> torch.Tensor:
+        slot = self.slots[handle % len(self.slots)]
+        slot["event"].synchronize()
+        t = slot["ticket"]
+        if t is not None and not t.ok():
+            # pair capacity exceeded (abrupt view change): render this frame again, exactly; later
+            # frames use (and graphs are re-captured for) the larger capacity
+            self.redone += 1
+            self._set_capacity(t.pairs)
+            with torch.no_grad(), torch.cuda.stream(slot["stream"]):
+                self._enqueue(slot, float(slot["cam"].tanfovx), float(slot["cam"].tanfovy), exact=True, in_capture=False)
+                slot["event"].record(slot["stream"])
+            slot["event"].synchronize()
+        slot["busy"] = False
+        return slot["frame_host"]
+
+    def in_flight_limit(self) -> int:
+        return len(self.slots)
+
+
 def render_sweep(cameras: Sequence[Camera], render_fn: Callable[[Camera], torch.Tensor],
                  on_frame: Optional[Callable[[int, torch.Tensor], None]] = None, gather: bool = False,
                  streams: int = 2):

@@ -106,3 +106,42 @@ def test_fused_photometric_loss_matches_torch():
         l2 = ref(); (l2 * 1.7).backward(); g2 = a.grad.clone()
         assert abs(float(l1) - float(l2)) < 1e-6 * max(1.0, abs(float(l2)))
         assert torch.allclose(g1, g2, rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("graphs", [True, False])
+def test_scene_renderer_host_frames_match_plain_path(graphs):
+    """sweep.SceneRenderer (host camera in, pinned 8-bit frame out, deferred pair check, one CUDA graph
+    per frame slot) returns exactly the frames of forward + export_rgb8, also across a view change that
+    overflows the captured pair capacity (frame rendered again, graphs re-captured)."""
+    from robosimgs_b200 import GaussianRasterizer, export_rgb8
+    from robosimgs_b200.cameras import camera_look_at, orbit_cameras
+    from robosimgs_b200.scenes import cube_scene, settings_from_camera
+    from robosimgs_b200.sweep import SceneRenderer
+    dev = torch.device("cuda:0")
+    sc, _ = cube_scene(P=60000, seed=9, degree=1)
+    scene = {k: getattr(sc, k).to(dev) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+    bg = torch.tensor([0.1, 0.2, 0.3], device=dev)
+    far = orbit_cameras(9, (0, 0, 0), 9.0, 50.0, 320, 240, seed=3)            # few pairs
+    near = [camera_look_at((0.2, 0.1, 2.2), (0, 0, 0), (0, 1, 0), 50.0, 320, 240)] * 3   # many more pairs
+    cams = far + near + far[:4]
+    from robosimgs_b200 import _cabi
+    _cabi.set_option("bin_shift", 0)           # 16-px bins: the near view has several times the pairs of the far ones
+    try:
+        r = SceneRenderer(scene, 1, bg, 240, 320, streams=2, graphs=graphs)
+        m2 = torch.zeros_like(scene["means3D"])
+        got, handles = [], []
+        for cam in cams:
+            while len(handles) >= r.in_flight_limit():
+                got.append(r.collect(handles.pop(0)).clone())
+            handles.append(r.submit(cam))
+        while handles:
+            got.append(r.collect(handles.pop(0)).clone())
+    finally:
+        _cabi.set_option("bin_shift", -1)
+    assert r.redone >= 1                       # the jump to the near camera overflowed the capacity
+    with torch.no_grad():
+        for cam, frame in zip(cams, got):
+            rs = settings_from_camera(cam, 1, bg=(0.1, 0.2, 0.3), device=dev)
+            col, _ = GaussianRasterizer(rs)(scene["means3D"], m2, scene["opacities"], shs=scene["shs"],
+                                            scales=scene["scales"], rotations=scene["rotations"])
+            assert torch.equal(export_rgb8(col).cpu(), frame)
