@@ -84,6 +84,7 @@ struct RenderBwdArgs {
 
 struct ProjectBwdArgs {
   int P, M, W, H, sh_vec;
+  int slab;   // in: -1 disables the shared-memory SH-gradient slab; set by the launcher
   float tanfovx, tanfovy, scale_modifier;
   const float *means, *scales, *rots, *shs, *cov3d_precomp;
   const float *view, *proj, *campos;
