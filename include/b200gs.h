@@ -229,13 +229,17 @@ int64_t b200gs_launch_count(int reset);
  *   "bin_shift": -1 automatic (default), 0..5 = sort pairs per (16 << shift)^2 pixel bins
  *   "binning":    1 bucketed binning (per-bin counters and cursors, one per-bin sort launch; default),
  *                 0 global radix sort of (bin << 32 | depth) keys
+ *   "sort_keys":  32 (default) global sort on 32-bit keys (bin << 24 | monotone 24-bit quantisation of the depth
+ *                 bits; exact (depth, index) order restored inside runs of equal keys) whenever there are at
+ *                 most 255 bins and the library sort is used -- four radix passes instead of five; 64 always
+ *                 sorts the public algorithm's 64-bit (bin << 32 | depth bits) keys
  *   "render":     1 compositing kernels with four pixels per thread (default), 0 one pixel per thread
  *   "gather":     1 LDGSTS record gather in the one-pixel compositing kernels (default), 0 TMA bulk copies
  *   "sort":       0 CUB radix sort, 1 automatic (default: single-launch cooperative radix sort for
  *                 pair lists <= 256 k, CUB above), 2 cooperative sort whenever the list is <= 3 M
  * Environment equivalents read at first use: B200GS_BIN_SHIFT, B200GS_GATHER=tma|ldgsts,
  * B200GS_SORT=cub|auto|coop,
- * B200GS_RENDER=4px|1px, B200GS_BINNING=bucket|sort.
+ * B200GS_RENDER=4px|1px, B200GS_BINNING=bucket|sort, B200GS_SORT_KEYS=64.
  */
 int b200gs_set_option(const char* name, int value);
 

@@ -136,6 +136,20 @@ static bool use_render4() {
   return m == 1;
 }
 
+// pair keys of the global sort: 32-bit (bin << 24 | quantised depth, exact order restored in the ranges
+// pass; default whenever there are at most 255 bins and the library sort is used) or 64-bit.
+// b200gs_set_option("sort_keys", 32|64), B200GS_SORT_KEYS=64.
+static std::atomic<int> g_key_mode{-1};
+static bool allow_key32() {
+  int m = g_key_mode.load();
+  if (m < 0) {
+    const char* e = getenv("B200GS_SORT_KEYS");
+    m = (e && atoi(e) == 64) ? 64 : 32;
+    g_key_mode.store(m);
+  }
+  return m == 32;
+}
+
 static int tile_bits_for(int num_tiles) {
   int bits = 1;
   while ((1 << bits) <= num_tiles) bits++;  // room for the invalid id == num_tiles
@@ -267,6 +281,10 @@ int b200gs_set_option(const char* name, int value) {
   }
   if (name && !strcmp(name, "sort")) {
     g_sort_mode.store(value < 0 ? 1 : (value > 2 ? 2 : value));
+    return 0;
+  }
+  if (name && !strcmp(name, "sort_keys")) {
+    g_key_mode.store(value == 64 ? 64 : 32);
     return 0;
   }
   if (name && !strcmp(name, "binning")) {
@@ -424,8 +442,9 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
       if ((rc2 = debug_sync(prm, st, "bin sort"))) return rc2;
     } else if (cap > 0) {
       if ((rc2 = check_cuda(cudaMemsetAsync(gb.counters, 0, 32 * sizeof(uint32_t), st), "clear counters"))) return rc2;
-      const int key_bits = 32 + tile_bits;
       const bool coop = use_coop_sort(cap);
+      const bool key32 = !coop && num_tiles <= 255 && allow_key32();
+      const int key_bits = key32 ? 24 + tile_bits : 32 + tile_bits;
       // the cooperative sort ping-pongs (passes) times; emit into whichever buffer makes the
       // result land in keys_sorted / vals_sorted
       const bool emit_into_sorted = coop && (((key_bits + 7) / 8) % 2 == 0);
@@ -434,6 +453,11 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
       EmitArgs ea;
       ea.P = P; ea.gx = gx; ea.gy = gy; ea.gbx = gbx; ea.bin_shift = bs;
       ea.invalid_tile = (uint32_t)num_tiles; ea.capacity = cap;
+      ea.key32 = key32 ? 1 : 0;
+      {
+        const float np = pa.near_plane;
+        memcpy(&ea.near_bits, &np, sizeof(uint32_t));
+      }
       ea.tiles = gb.tiles; ea.offsets = gb.offsets; ea.depth_key = gb.depth_key; ea.rec = gb.rec; ea.radii = radii;
       ea.keys = emit_keys; ea.vals = emit_vals;
       ea.big_queue = gb.big_queue; ea.big_count = gb.counters;
@@ -449,16 +473,27 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
           uint32_t* other_vals = emit_into_sorted ? bb.vals : bb.vals_sorted;
           if ((rc2 = coop_sort_pairs(emit_keys, emit_vals, other_keys, other_vals, bb.coop_hist, cap, key_bits, st)))
             return rc2;
-        } else if ((rc2 = sort_pairs(bb, cap, key_bits, st))) {
+        } else if ((rc2 = key32 ? sort_pairs32(bb, cap, key_bits, st) : sort_pairs(bb, cap, key_bits, st))) {
           return rc2;
         }
       }
       if ((rc2 = debug_sync(prm, st, "pair sort"))) return rc2;
-      RangesArgs ga;
-      ga.D = cap; ga.num_tiles = (uint32_t)num_tiles; ga.keys_sorted = bb.keys_sorted; ga.ranges = ib.ranges;
       {
         StageTimer t(4, st);
-        launch_tile_ranges(ga, st);
+        if (key32) {
+          Ranges32Args ga;
+          ga.D = cap; ga.num_tiles = (uint32_t)num_tiles; ga.id_bits = ba.id_bits;
+          ga.keys_sorted = reinterpret_cast<const uint32_t*>(bb.keys_sorted); ga.vals_sorted = bb.vals_sorted;
+          ga.depth_key = gb.depth_key; ga.ranges = ib.ranges;
+          // after the sort the unsorted value array and both key arrays are free: run queue and scratch
+          ga.run_queue = reinterpret_cast<uint2*>(bb.vals); ga.run_capacity = cap / 2; ga.run_count = gb.counters + 3;
+          ga.scratch_a = bb.keys; ga.scratch_b = bb.keys_sorted;
+          launch_tile_ranges32(ga, st);
+        } else {
+          RangesArgs ga;
+          ga.D = cap; ga.num_tiles = (uint32_t)num_tiles; ga.keys_sorted = bb.keys_sorted; ga.ranges = ib.ranges;
+          launch_tile_ranges(ga, st);
+        }
       }
       if ((rc2 = debug_sync(prm, st, "tile ranges"))) return rc2;
     }

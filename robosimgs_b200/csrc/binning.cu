@@ -23,7 +23,10 @@ size_t pair_sort_temp_bytes(int64_t D, int key_bits) {
   size_t a = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, a, (const uint64_t*)nullptr, (uint64_t*)nullptr,
                                   (const uint32_t*)nullptr, (uint32_t*)nullptr, D, 0, key_bits);
-  return a;
+  size_t b = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, b, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                  (const uint32_t*)nullptr, (uint32_t*)nullptr, D, 0, 32);
+  return a > b ? a : b;
 }
 
 int scan_bin_counts(const GeomBuf& g, int P, cudaStream_t st) {
@@ -43,6 +46,19 @@ int sort_pairs(const BinBuf& b, int64_t D, int key_bits, cudaStream_t st) {
   if (check_cuda(cub::DeviceRadixSort::SortPairs(b.cub_temp, tb, (const uint64_t*)b.keys, b.keys_sorted,
                                                  (const uint32_t*)b.vals, b.vals_sorted, D, 0, key_bits, st),
                  "pair sort"))
+    return B200GS_ERR_CUDA;
+  count_launch(1 + (key_bits + 7) / 8);
+  return 0;
+}
+
+// 32-bit keys (bin << 24 | quantised depth) stored in the first halves of the 64-bit key arrays: four passes.
+int sort_pairs32(const BinBuf& b, int64_t D, int key_bits, cudaStream_t st) {
+  if (D == 0) return 0;
+  size_t tb = b.cub_temp_bytes;
+  if (check_cuda(cub::DeviceRadixSort::SortPairs(b.cub_temp, tb, reinterpret_cast<const uint32_t*>(b.keys),
+                                                 reinterpret_cast<uint32_t*>(b.keys_sorted), (const uint32_t*)b.vals,
+                                                 b.vals_sorted, D, 0, key_bits, st),
+                 "pair sort (32-bit keys)"))
     return B200GS_ERR_CUDA;
   count_launch(1 + (key_bits + 7) / 8);
   return 0;

@@ -23,6 +23,8 @@ struct EmitArgs {
   int P, gx, gy;     // gx, gy: 16-px tile grid (reference rect)
   int gbx, bin_shift; // bin grid width, log2(bin edge / 16)
   uint32_t invalid_tile;
+  int key32;            // 32-bit pair keys (bin << 24 | quantised depth), see project.cu:put_key
+  uint32_t near_bits;   // IEEE bits of the near plane (origin of the depth quantisation)
   uint32_t capacity;   // number of pair slots in keys/vals; slots [D, capacity) are padded
   const uint32_t *tiles, *offsets, *depth_key;
   const float4* rec;
@@ -55,6 +57,20 @@ struct RangesArgs {
   uint32_t num_tiles;
   const uint64_t* keys_sorted;
   uint2* ranges;
+};
+
+struct Ranges32Args {
+  int64_t D;
+  uint32_t num_tiles;
+  int id_bits;
+  const uint32_t* keys_sorted;   // (bin << 24 | q24), sorted
+  uint32_t* vals_sorted;         // Gaussian ids; runs of equal keys are re-ordered in place
+  const uint32_t* depth_key;     // [P] exact depth bits
+  uint2* ranges;
+  uint2* run_queue;              // long runs (start, length)
+  uint32_t run_capacity;
+  uint32_t* run_count;
+  uint64_t *scratch_a, *scratch_b;   // [D] each, free after the sort
 };
 
 struct RenderArgs {
@@ -99,6 +115,7 @@ struct ProjectBwdArgs {
 void launch_project(const ProjectArgs& a, int deg, cudaStream_t st);
 void launch_emit_pairs(const EmitArgs& a, cudaStream_t st);
 void launch_tile_ranges(const RangesArgs& a, cudaStream_t st);
+void launch_tile_ranges32(const Ranges32Args& a, cudaStream_t st);
 void launch_mark_visible(int P, const float* means, const float* view, float near_plane, uint8_t* present,
                          cudaStream_t st);
 void launch_extract_alpha(const float4* pix, size_t npx, float* out, cudaStream_t st);
@@ -148,5 +165,6 @@ size_t scan_temp_bytes(int P);
 size_t pair_sort_temp_bytes(int64_t D, int key_bits);
 int scan_bin_counts(const GeomBuf& g, int P, cudaStream_t st);
 int sort_pairs(const BinBuf& b, int64_t D, int key_bits, cudaStream_t st);
+int sort_pairs32(const BinBuf& b, int64_t D, int key_bits, cudaStream_t st);   // 32-bit keys in keys / keys_sorted
 
 }  // namespace b200gs

@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "kernels.cuh"
 #include "spans.cuh"
+#include "binsort.cuh"
 
 namespace b200gs {
 
@@ -251,6 +252,25 @@ __global__ void __launch_bounds__(256, PROJECT_MIN_BLOCKS) k_project(ProjectArgs
 // K3: emit ((bin << 32) | depth bits, Gaussian id) pairs in index order; offsets[] is the inclusive
 // scan of the per-Gaussian bin counts.
 // ==================================================================================================
+// Pair key.  64-bit form: (bin << 32) | depth bits -- the public algorithm's key.  32-bit form (bins <=
+// 255): (bin << 24) | q24, q24 = min((depth bits - near-plane bits) >> 3, 2^24 - 1), a monotone
+// quantisation of the positive-float depth order that only merges depths within 8 ulps (or beyond
+// 2^16 x near).  A stable sort on it needs FOUR 8-bit passes over 8-byte pairs instead of five over
+// 12-byte pairs; k_tile_ranges32 then restores the exact (depth bits, index) order inside the rare runs of
+// equal keys, so the result is identical.
+__device__ __forceinline__ uint32_t quant24(uint32_t depth_bits, uint32_t near_bits) {
+  const uint32_t d = depth_bits > near_bits ? depth_bits - near_bits : 0u;
+  return min(d >> 3, 0xFFFFFFu);
+}
+__device__ __forceinline__ void put_key(const EmitArgs& a, uint32_t o, uint32_t bin, uint32_t depth_bits) {
+  if (a.key32) reinterpret_cast<uint32_t*>(a.keys)[o] = (bin << 24) | quant24(depth_bits, a.near_bits);
+  else a.keys[o] = ((uint64_t)bin << 32) | depth_bits;
+}
+__device__ __forceinline__ void put_invalid_key(const EmitArgs& a, uint32_t o) {
+  if (a.key32) reinterpret_cast<uint32_t*>(a.keys)[o] = a.invalid_tile << 24;
+  else a.keys[o] = (uint64_t)a.invalid_tile << 32;
+}
+
 __global__ void __launch_bounds__(256) k_emit_pairs(EmitArgs a) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t cap = a.capacity;
@@ -258,7 +278,7 @@ __global__ void __launch_bounds__(256) k_emit_pairs(EmitArgs a) {
   uint32_t n = 0, off = 0;
   float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
   int radius = 0;
-  uint64_t depth = 0;
+  uint32_t depth = 0;
   if (r < a.P) {
     n = a.tiles[r];
     if (n) {
@@ -282,7 +302,7 @@ __global__ void __launch_bounds__(256) k_emit_pairs(EmitArgs a) {
         row_span(s, rect, ty, c0, c1);
         for (int tx = c0; tx < c1 && o < end; tx++, o++) {
           if (o < cap) {
-            a.keys[o] = ((uint64_t)(uint32_t)(ty * a.gbx + tx) << 32) | depth;
+            put_key(a, o, (uint32_t)(ty * a.gbx + tx), depth);
             a.vals[o] = g;
           }
         }
@@ -290,7 +310,7 @@ __global__ void __launch_bounds__(256) k_emit_pairs(EmitArgs a) {
     }
     // defensive: never leave unwritten slots (count and emit share row_span, so o == end)
     for (; o < end; o++) {
-      if (o < cap) { a.keys[o] = (uint64_t)a.invalid_tile << 32; a.vals[o] = g; }
+      if (o < cap) { put_invalid_key(a, o); a.vals[o] = g; }
     }
   }
   // ---- large footprints go to a global queue; k_emit_big emits them one warp per Gaussian so a
@@ -302,7 +322,7 @@ __global__ void __launch_bounds__(256) k_emit_pairs(EmitArgs a) {
     const uint32_t D = a.P > 0 ? a.offsets[a.P - 1] : 0u;
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = D + (uint32_t)r; i < cap; i += stride) {
-      a.keys[i] = (uint64_t)a.invalid_tile << 32;
+      put_invalid_key(a, i);
       a.vals[i] = 0u;
     }
   }
@@ -321,7 +341,7 @@ __global__ void __launch_bounds__(256) k_emit_big(EmitArgs a) {
     const uint32_t g = a.big_queue[w];
     const uint32_t n = a.tiles[g];
     const uint32_t off = a.offsets[g] - n, end = off + n;
-    const uint64_t depth = a.depth_key[g];
+    const uint32_t depth = a.depth_key[g];
     const float4 q0 = a.rec[(size_t)g * REC_F4], q1 = a.rec[(size_t)g * REC_F4 + 1];
     const TileRect rect = bin_rect(reference_rect(q0.x, q0.y, a.radii[g], a.gx, a.gy), a.bin_shift);
     SpanCtx s;
@@ -349,7 +369,7 @@ __global__ void __launch_bounds__(256) k_emit_big(EmitArgs a) {
         for (uint32_t k = lane; k < l_i; k += 32) {
           const uint32_t idx = o_i + k;
           if (idx < end && idx < cap) {
-            a.keys[idx] = ((uint64_t)(tile0 + k) << 32) | depth;
+            put_key(a, idx, tile0 + k, depth);
             a.vals[idx] = g;
           }
         }
@@ -357,7 +377,7 @@ __global__ void __launch_bounds__(256) k_emit_big(EmitArgs a) {
       o += __shfl_sync(0xffffffffu, incl, 31);
     }
     for (uint32_t idx = min(o, end) + lane; idx < end; idx += 32) {
-      if (idx < cap) { a.keys[idx] = (uint64_t)a.invalid_tile << 32; a.vals[idx] = g; }
+      if (idx < cap) { put_invalid_key(a, idx); a.vals[idx] = g; }
     }
   }
 }
@@ -372,6 +392,71 @@ __global__ void __launch_bounds__(256) k_tile_ranges(RangesArgs a) {
   if (t >= a.num_tiles) return;   // padding of the speculative capacity
   if (j == 0 || (uint32_t)(a.keys_sorted[j - 1] >> 32) != t) a.ranges[t].x = (uint32_t)j;
   if (j == a.D - 1 || (uint32_t)(a.keys_sorted[j + 1] >> 32) != t) a.ranges[t].y = (uint32_t)(j + 1);
+}
+
+// K5 for 32-bit keys: per-bin ranges + exact order inside runs of equal keys.  A run holds pairs of one
+// bin whose depths quantised alike; the stable sort left them in emission (= index) order, the exact
+// order is (depth bits, index).  The head of a run repairs it: short runs by insertion on
+// (depth_key[id], id); long runs (a fronto-parallel planar scene) are queued for k_fix_long_runs.
+constexpr uint32_t TIE_INSERTION_MAX = 24;
+
+__global__ void __launch_bounds__(256) k_tile_ranges32(Ranges32Args a) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= a.D) return;
+  const uint32_t key = a.keys_sorted[j];
+  const uint32_t t = key >> 24;
+  if (t >= a.num_tiles) return;   // padding of the speculative capacity
+  const bool has_prev = j > 0, has_next = j + 1 < a.D;
+  const uint32_t prev = has_prev ? a.keys_sorted[j - 1] : 0u, next = has_next ? a.keys_sorted[j + 1] : 0u;
+  if (!has_prev || (prev >> 24) != t) a.ranges[t].x = (uint32_t)j;
+  if (!has_next || (next >> 24) != t) a.ranges[t].y = (uint32_t)(j + 1);
+  if (!(has_next && next == key) || (has_prev && prev == key)) return;   // not the head of a run
+  int64_t e = j + 2;
+  while (e < a.D && a.keys_sorted[e] == key) e++;
+  const uint32_t len = (uint32_t)(e - j);
+  uint32_t* v = a.vals_sorted + j;
+  if (len > TIE_INSERTION_MAX) {
+    const uint32_t q = atomicAdd(a.run_count, 1u);
+    if (q < a.run_capacity) { a.run_queue[q] = make_uint2((uint32_t)j, len); return; }
+  }
+  for (uint32_t x = 1; x < len; x++) {
+    const uint32_t id = v[x];
+    const uint64_t k = ((uint64_t)a.depth_key[id] << 32) | id;
+    uint32_t y = x;
+    while (y > 0) {
+      const uint32_t pid = v[y - 1];
+      if ((((uint64_t)a.depth_key[pid] << 32) | pid) <= k) break;
+      v[y] = pid;
+      y--;
+    }
+    v[y] = id;
+  }
+}
+
+// One CTA per queued long run: sort it on the full (depth bits << 32 | index) key with the one-CTA radix
+// passes of binsort.cuh (index digits first, then the depth word), scratch = the two key arrays the
+// global sort no longer needs.
+__global__ void __launch_bounds__(BS_THREADS) k_fix_long_runs(Ranges32Args a) {
+  __shared__ BinSortShared sh;
+  const uint32_t count = min(*a.run_count, a.run_capacity);
+  for (uint32_t q = blockIdx.x; q < count; q += gridDim.x) {
+    const uint2 run = a.run_queue[q];
+    const uint32_t n = run.y;
+    uint64_t* A = a.scratch_a + run.x;
+    uint64_t* B = a.scratch_b + run.x;
+    uint32_t* v = a.vals_sorted + run.x;
+    for (uint32_t i = threadIdx.x; i < n; i += BS_THREADS) {
+      const uint32_t id = v[i];
+      A[i] = ((uint64_t)a.depth_key[id] << 32) | id;
+    }
+    __syncthreads();
+    int passes = 0;
+    for (int s = 0; s < a.id_bits; s += 8, passes++) bin_sort_pass(sh, (passes & 1) ? B : A, (passes & 1) ? A : B, n, s);
+    for (int p = 0; p < 4; p++, passes++) bin_sort_pass(sh, (passes & 1) ? B : A, (passes & 1) ? A : B, n, 32 + 8 * p);
+    const uint64_t* F = (passes & 1) ? B : A;
+    for (uint32_t i = threadIdx.x; i < n; i += BS_THREADS) v[i] = (uint32_t)__ldcg(F + i);
+    __syncthreads();
+  }
 }
 
 // ==================================================================================================
@@ -688,6 +773,13 @@ void launch_tile_ranges(const RangesArgs& a, cudaStream_t st) {
   if (a.D == 0) return;
   k_tile_ranges<<<(unsigned)((a.D + 255) / 256), 256, 0, st>>>(a);
   count_launch();
+}
+
+void launch_tile_ranges32(const Ranges32Args& a, cudaStream_t st) {
+  if (a.D == 0) return;
+  k_tile_ranges32<<<(unsigned)((a.D + 255) / 256), 256, 0, st>>>(a);
+  k_fix_long_runs<<<148, BS_THREADS, 0, st>>>(a);
+  count_launch(2);
 }
 
 void launch_mark_visible(int P, const float* means, const float* view, float near_plane, uint8_t* present,

@@ -277,24 +277,27 @@ def test_bin_shift_gather_and_sort_modes_never_change_results():
     w = torch.rand(3, 300, 400, generator=torch.Generator().manual_seed(17))
     base = None
     try:
-        # (binning, gather, sort): bucketed per-bin sort / global radix sort (cooperative, CUB)
-        for binning, gather, sort in ((1, 1, 1), (0, 1, 2), (0, 0, 2), (0, 1, 0)):
+        # (binning, gather, sort, key width): bucketed per-bin sort / global radix sort (cooperative; CUB with
+        # 32-bit quantised keys + exact tie repair -- used when there are <= 255 bins -- or 64-bit keys)
+        for binning, gather, sort, keys in ((1, 1, 1, 32), (0, 1, 2, 32), (0, 0, 2, 32), (0, 1, 0, 32), (0, 1, 0, 64)):
             for shift in (-1, 0, 1, 2, 3, 5):
                 _cabi.set_option("binning", binning)
                 _cabi.set_option("gather", gather)
                 _cabi.set_option("sort", sort)
+                _cabi.set_option("sort_keys", keys)
                 _cabi.set_option("bin_shift", shift)
                 color, radii, grads = gpu_render(sc, cam, 2, bg=(0.2, 0.1, 0.4), grad_weight=w)
                 if base is None:
                     base = (color, radii, grads)
                     continue
-                assert np.array_equal(color, base[0]) and np.array_equal(radii, base[1]), (binning, gather, sort, shift)
+                assert np.array_equal(color, base[0]) and np.array_equal(radii, base[1]), (binning, gather, sort, keys, shift)
                 for k in ("means3D", "shs", "opacities", "scales", "rotations"):
-                    assert max_rel_err(grads[k], base[2][k]) < 1e-5, (binning, gather, sort, shift, k)
+                    assert max_rel_err(grads[k], base[2][k]) < 1e-5, (binning, gather, sort, keys, shift, k)
     finally:
         _cabi.set_option("binning", -1)
         _cabi.set_option("gather", 1)
         _cabi.set_option("sort", 1)
+        _cabi.set_option("sort_keys", 32)
         _cabi.set_option("bin_shift", -1)
 
 
@@ -322,14 +325,20 @@ def test_equal_depths_keep_index_order_in_both_binning_pipelines():
             st = _oracle(rs, sc)
             assert len(np.unique(st.depths[st.radii > 0])) <= levels
             imgs = []
-            for binning in (1, 0):
+            # bucketed; global CUB sort with 32-bit keys (tie runs repaired: long runs by k_fix_long_runs, short
+            # ones by insertion) and with 64-bit keys; cooperative sort
+            for binning, sort, keys in ((1, 1, 32), (0, 0, 32), (0, 0, 64), (0, 2, 32)):
                 _cabi.set_option("binning", binning)
+                _cabi.set_option("sort", sort)
+                _cabi.set_option("sort_keys", keys)
                 color, radii, _ = gpu_render(sc, cam, 0, bg=(0.1, 0.1, 0.1))
-                assert psnr(color, st.color) >= PSNR_MIN, (levels, binning)
+                assert psnr(color, st.color) >= PSNR_MIN, (levels, binning, sort, keys)
                 imgs.append(color)
-            assert np.array_equal(imgs[0], imgs[1]), levels
+            assert all(np.array_equal(imgs[0], im) for im in imgs[1:]), levels
     finally:
         _cabi.set_option("binning", -1)
+        _cabi.set_option("sort", 1)
+        _cabi.set_option("sort_keys", 32)
 
 
 def test_one_and_four_pixel_compositing_kernels_agree():
