@@ -169,7 +169,7 @@ int b200gs_transform_gaussians(int32_t n, const float* means_in, const float* ro
 
 /*
  * Training-step neighbour: photometric loss between a rendered image and its
- * target, n floats each (n % 4 == 0, 16-byte aligned).
+ * target, n floats each (16-byte aligned).
  *   forward : *out_sum = sum_i w_l2 (a_i-b_i)^2 + w_l1 |a_i-b_i|        (one pass, device scalar)
  *   backward: dL_da_i  = *upstream * scale * (2 w_l2 (a_i-b_i) + w_l1 sign(a_i-b_i))
  */
@@ -233,13 +233,14 @@ int64_t b200gs_launch_count(int reset);
  *                 bits; exact (depth, index) order restored inside runs of equal keys) whenever there are at
  *                 most 255 bins and the library sort is used -- four radix passes instead of five; 64 always
  *                 sorts the public algorithm's 64-bit (bin << 32 | depth bits) keys
- *   "render":     1 compositing kernels with four pixels per thread (default), 0 one pixel per thread
+ *   "render":     -1 automatic (default: four pixels per thread from 4096 tiles up, one pixel per thread
+ *                 below), 1 compositing kernels with four pixels per thread, 0 one pixel per thread
  *   "gather":     1 LDGSTS record gather in the one-pixel compositing kernels (default), 0 TMA bulk copies
  *   "sort":       0 CUB radix sort, 1 automatic (default: single-launch cooperative radix sort for
  *                 pair lists <= 256 k, CUB above), 2 cooperative sort whenever the list is <= 3 M
  * Environment equivalents read at first use: B200GS_BIN_SHIFT, B200GS_GATHER=tma|ldgsts,
  * B200GS_SORT=cub|auto|coop,
- * B200GS_RENDER=4px|1px, B200GS_BINNING=bucket|sort, B200GS_SORT_KEYS=64.
+ * B200GS_RENDER=auto|4px|1px, B200GS_BINNING=bucket|sort, B200GS_SORT_KEYS=64.
  */
 int b200gs_set_option(const char* name, int value);
 

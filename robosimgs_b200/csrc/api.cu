@@ -123,17 +123,22 @@ static bool use_coop_sort(int64_t n) {
   return n <= (m == 2 ? COOP_SORT_MAX_ITEMS : COOP_SORT_AUTO_MAX);
 }
 
-// compositing kernels: 1 = four pixels per thread (render4.cu, default), 0 = one pixel per thread
-// (render.cu).  B200GS_RENDER=1px|4px or b200gs_set_option("render", 0|1).
-static std::atomic<int> g_render_mode{-1};
-static bool use_render4() {
+// compositing kernels: 1 = four pixels per thread (render4.cu: two warps per tile, about half the
+// instructions per pixel), 0 = one pixel per thread (render.cu: eight warps per tile), -1 = automatic
+// (default): the four-pixel kernels need enough tiles to fill the GPU with two warps each -- at 1080p
+// (8160 tiles) they are 1.6-1.9x faster, at 800x800 (2500 tiles, one partial wave of 64-thread CTAs) the
+// one-pixel kernels win by up to 1.6x because four times as many warps hide the latency of each tile's
+// serial list walk.  B200GS_RENDER=1px|4px|auto or b200gs_set_option("render", 0|1|-1).
+static std::atomic<int> g_render_mode{-2};
+constexpr int RENDER4_MIN_TILES = 4096;
+static bool use_render4(int num_tiles16) {
   int m = g_render_mode.load();
-  if (m < 0) {
+  if (m == -2) {
     const char* e = getenv("B200GS_RENDER");
-    m = (e && e[0] == '1') ? 0 : 1;
+    m = !e ? -1 : (!strcmp(e, "1px") ? 0 : (!strcmp(e, "4px") ? 1 : -1));
     g_render_mode.store(m);
   }
-  return m == 1;
+  return m < 0 ? num_tiles16 >= RENDER4_MIN_TILES : m == 1;
 }
 
 // pair keys of the global sort: 32-bit (bin << 24 | quantised depth, exact order restored in the ranges
@@ -292,7 +297,7 @@ int b200gs_set_option(const char* name, int value) {
     return 0;
   }
   if (name && !strcmp(name, "render")) {
-    g_render_mode.store(value == 0 ? 0 : 1);
+    g_render_mode.store(value < 0 ? -1 : (value == 0 ? 0 : 1));
     return 0;
   }
   if (name && !strcmp(name, "gather")) {
@@ -504,7 +509,7 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
     ra.vec4 = ((W & 3) == 0 && (reinterpret_cast<uintptr_t>(out_color) & 15) == 0) ? 1 : 0;
     {
       StageTimer t(5, st);
-      if (use_render4()) launch_render4(ra, st);
+      if (use_render4(gx * gy)) launch_render4(ra, st);
       else launch_render(ra, st);
     }
     return debug_sync(prm, st, "render");
@@ -601,7 +606,7 @@ int b200gs_backward(const B200GSParams* prm, const float* bg, const float* viewm
     ra.vec4 = ((W & 3) == 0 && (reinterpret_cast<uintptr_t>(dL_dout_color) & 15) == 0) ? 1 : 0;
     {
       StageTimer t(6, st);
-      if (use_render4()) launch_render_bwd4(ra, st);
+      if (use_render4(gx * gy)) launch_render_bwd4(ra, st);
       else launch_render_bwd(ra, st);
     }
     if ((rc = debug_sync(prm, st, "render backward"))) return rc;
@@ -626,9 +631,9 @@ int b200gs_backward(const B200GSParams* prm, const float* bg, const float* viewm
 }
 
 static int check_loss_args(const float* a, const float* b, int64_t n, const void* o) {
-  if (n < 0 || (n & 3) || (n > 0 && (!a || !b || !o)) || (reinterpret_cast<uintptr_t>(a) & 15) ||
+  if (n < 0 || (n > 0 && (!a || !b || !o)) || (reinterpret_cast<uintptr_t>(a) & 15) ||
       (reinterpret_cast<uintptr_t>(b) & 15)) {
-    set_error("photometric_loss: need n %% 4 == 0 and 16-byte aligned non-NULL buffers");
+    set_error("photometric_loss: need 16-byte aligned non-NULL buffers");
     return B200GS_ERR_INVALID_ARG;
   }
   return 0;

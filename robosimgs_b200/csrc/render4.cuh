@@ -1,0 +1,117 @@
+// render4.cuh -- pieces shared by the four-pixels-per-thread compositing kernels (render4.cu: one survivor
+// list per 16x8 warp block; render4q.cu: one list per 8x4 quarter of it).
+#pragma once
+#include <type_traits>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace b200gs {
+
+
+constexpr int R4_CH = 64;       // records per ring stage == threads per CTA
+#ifndef R4_STAGES_N
+#define R4_STAGES_N 2
+#endif
+constexpr int R4_STAGES = R4_STAGES_N;
+constexpr int R4_THREADS = 64;
+constexpr float LOG2E = 1.4426950408889634f;
+
+// identical to render.cu (kept local: both translation units inline it)
+__device__ __forceinline__ bool r4_block_may_contribute(float x, float y, float A, float B, float C, float thr,
+                                                        float x0, float y0, float x1, float y1) {
+  const float cx = clampf(x, x0, x1), cy = clampf(y, y0, y1);
+  const float dxe = cx - x, dye = cy - y;
+  float dy1 = clampf(y - B * dxe * rcp_fast(C), y0, y1) - y;
+  const float q1 = A * dxe * dxe + 2.f * B * dxe * dy1 + C * dy1 * dy1;
+  float dx2 = clampf(x - B * dye * rcp_fast(A), x0, x1) - x;
+  const float q2 = A * dx2 * dx2 + 2.f * B * dx2 * dye + C * dye * dye;
+  const float q = fminf(q1, q2);
+  const float mag = fabsf(A) * (dxe * dxe + dx2 * dx2) + fabsf(C) * (dye * dye + dy1 * dy1);
+  return 0.5f * q - 4e-6f * mag <= thr;
+}
+
+__device__ __forceinline__ bool r4_tile_in_reference_rect(float px, float py, float fr, int tx, int ty, int gx,
+                                                          int gy) {
+  const int x0 = min(gx, max(0, (int)((px - fr) / TILE)));
+  const int y0 = min(gy, max(0, (int)((py - fr) / TILE)));
+  const int x1 = min(gx, max(0, (int)((px + fr + (TILE - 1)) / TILE)));
+  const int y1 = min(gy, max(0, (int)((py + fr + (TILE - 1)) / TILE)));
+  return tx >= x0 && tx < x1 && ty >= y0 && ty < y1;
+}
+
+__device__ __forceinline__ void r4_cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void r4_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void r4_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ float ex2_fast(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// Ring of gathered records: thread t owns slot t of every stage; the Gaussian id of the next fill
+// is prefetched one chunk ahead.  One cp.async group is committed per issue() (possibly empty), so
+// "chunk c resident" == "at most R4_STAGES-1 groups pending".
+struct Ring4 {
+  float4 (*sm)[R4_CH * REC_F4];
+  const uint32_t* list;
+  const float4* rec;
+  uint32_t n, nchunks;
+  uint32_t next_id;
+  int tid;
+
+  __device__ __forceinline__ uint32_t count(uint32_t c) const { return min((uint32_t)R4_CH, n - c * R4_CH); }
+  __device__ __forceinline__ uint32_t load_id(uint32_t c) const {
+    return (c < nchunks && (uint32_t)tid < count(c)) ? __ldg(list + c * R4_CH + tid) : 0u;
+  }
+  __device__ __forceinline__ void issue(uint32_t c, uint32_t id) {
+    if (c < nchunks && (uint32_t)tid < count(c)) {
+      const float4* src = rec + (size_t)id * REC_F4;
+      float4* dst = &sm[c % R4_STAGES][tid * REC_F4];
+      r4_cp_async16(dst, src);
+      r4_cp_async16(dst + 1, src + 1);
+      r4_cp_async16(dst + 2, src + 2);
+    }
+    r4_cp_async_commit();
+  }
+  __device__ __forceinline__ void prologue() {
+    uint32_t ids[R4_STAGES];
+#pragma unroll
+    for (int s = 0; s < R4_STAGES; s++) ids[s] = load_id(s);
+#pragma unroll
+    for (int s = 0; s < R4_STAGES; s++) issue(s, ids[s]);
+    next_id = load_id(R4_STAGES);
+  }
+  __device__ __forceinline__ void wait() {
+    r4_cp_async_wait<R4_STAGES - 1>();
+    __syncthreads();
+  }
+  // stage c % R4_STAGES is free (caller synchronised the CTA): refill it with chunk c + R4_STAGES
+  __device__ __forceinline__ void refill(uint32_t c) {
+    issue(c + R4_STAGES, next_id);
+    next_id = load_id(c + R4_STAGES + 1);
+  }
+};
+
+// Per-record terms shared by the four pixels of a thread (a row): with the conic scaled by
+// log2(e), power*log2(e) = -dx*(hA*dx + B*dy) - hC*dy^2.  Explicitly rounded so the forward and the
+// adjoint evaluate bit-identical alphas (the adjoint re-derives which records contributed).
+struct RowTerms {
+  float hA, bdy, cdy2;
+};
+__device__ __forceinline__ RowTerms row_terms(float A, float B, float C, float dy) {
+  RowTerms r;
+  r.hA = __fmul_rn(A, 0.5f * LOG2E);
+  r.bdy = __fmul_rn(__fmul_rn(B, LOG2E), dy);
+  r.cdy2 = __fmul_rn(__fmul_rn(__fmul_rn(C, 0.5f * LOG2E), dy), dy);
+  return r;
+}
+__device__ __forceinline__ float power2_of(const RowTerms& r, float dx) {
+  return __fmaf_rn(-dx, __fmaf_rn(r.hA, dx, r.bdy), -r.cdy2);
+}
+
+
+}  // namespace b200gs

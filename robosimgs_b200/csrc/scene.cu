@@ -75,12 +75,18 @@ __global__ void __launch_bounds__(256) k_transform_gaussians(int n, const float*
 // loss = sum_i w_l2 * (a_i - b_i)^2 + w_l1 * |a_i - b_i|   (caller divides by n for the mean);
 // one pass over image and target, block reduction, one atomic per block.
 __global__ void __launch_bounds__(256) k_photometric_loss(const float4* __restrict__ a, const float4* __restrict__ b,
-                                                          size_t n4, float w_l2, float w_l1, float* __restrict__ out) {
+                                                          size_t n4, size_t n, float w_l2, float w_l1,
+                                                          float* __restrict__ out) {
   float acc = 0.f;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     const float4 x = __ldg(a + i), y = __ldg(b + i);
     const float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
     acc += w_l2 * (d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3) + w_l1 * (fabsf(d0) + fabsf(d1) + fabsf(d2) + fabsf(d3));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {     // up to three tail elements
+    const size_t i = n4 * 4 + threadIdx.x;
+    const float d = reinterpret_cast<const float*>(a)[i] - reinterpret_cast<const float*>(b)[i];
+    acc += w_l2 * d * d + w_l1 * fabsf(d);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -96,10 +102,14 @@ __global__ void __launch_bounds__(256) k_photometric_loss(const float4* __restri
 
 // dL/da_i = g * (2 w_l2 (a_i - b_i) + w_l1 sign(a_i - b_i)),  g = *upstream (device scalar) * scale
 __global__ void __launch_bounds__(256) k_photometric_loss_bwd(const float4* __restrict__ a, const float4* __restrict__ b,
-                                                              size_t n4, float w_l2, float w_l1, float scale,
+                                                              size_t n4, size_t n, float w_l2, float w_l1, float scale,
                                                               const float* __restrict__ upstream, float4* __restrict__ g) {
   const float u = __ldg(upstream) * scale;
   auto f = [&](float d) { return u * (2.f * w_l2 * d + w_l1 * ((d > 0.f) - (d < 0.f))); };
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const size_t i = n4 * 4 + threadIdx.x;
+    reinterpret_cast<float*>(g)[i] = f(reinterpret_cast<const float*>(a)[i] - reinterpret_cast<const float*>(b)[i]);
+  }
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     const float4 x = __ldg(a + i), y = __ldg(b + i);
     g[i] = make_float4(f(x.x - y.x), f(x.y - y.y), f(x.z - y.z), f(x.w - y.w));
@@ -111,7 +121,7 @@ void launch_photometric_loss(const float* a, const float* b, size_t n, float w_l
   cudaMemsetAsync(out, 0, sizeof(float), st);
   if (n == 0) return;
   k_photometric_loss<<<148 * 8, 256, 0, st>>>(reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b),
-                                              n / 4, w_l2, w_l1, out);
+                                              n / 4, n, w_l2, w_l1, out);
   count_launch();
 }
 
@@ -119,7 +129,7 @@ void launch_photometric_loss_bwd(const float* a, const float* b, size_t n, float
                                  const float* upstream, float* g, cudaStream_t st) {
   if (n == 0) return;
   k_photometric_loss_bwd<<<148 * 8, 256, 0, st>>>(reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b),
-                                                  n / 4, w_l2, w_l1, scale, upstream, reinterpret_cast<float4*>(g));
+                                                  n / 4, n, w_l2, w_l1, scale, upstream, reinterpret_cast<float4*>(g));
   count_launch();
 }
 

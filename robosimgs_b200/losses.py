@@ -26,8 +26,8 @@ class _PhotometricLoss(torch.autograd.Function):
         a = img.contiguous()
         b = target.detach().to(torch.float32).contiguous()
         n = a.numel()
-        if a.dtype != torch.float32 or b.shape != a.shape or n % 4:
-            raise ValueError("photometric_loss: float32 tensors of equal shape with numel % 4 == 0 expected")
+        if a.dtype != torch.float32 or b.shape != a.shape:
+            raise ValueError("photometric_loss: float32 tensors of equal shape expected")
         out = torch.empty((), dtype=torch.float32, device=a.device)
         p = lambda t: C.c_void_p(t.data_ptr())
         with torch.cuda.device(a.device):

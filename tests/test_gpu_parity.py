@@ -24,6 +24,16 @@ def _need_gpu(built):
     _cabi.lib()   # fail loudly if the extension is missing
 
 
+@pytest.fixture(autouse=True, params=["auto", "4px"])
+def _compositing_kernels(request):
+    """Every test runs twice: with the automatic kernel choice (one pixel per thread on these small images)
+    and with the four-pixels-per-thread kernels forced (what 1080p frames use)."""
+    from robosimgs_b200 import _cabi
+    _cabi.set_option("render", -1 if request.param == "auto" else 1)
+    yield
+    _cabi.set_option("render", -1)
+
+
 def _oracle(rs, sc, dtype=np.float64, **kw):
     from oracle import gs_oracle
     if not kw:
@@ -342,7 +352,7 @@ def test_equal_depths_keep_index_order_in_both_binning_pipelines():
 
 
 def test_one_and_four_pixel_compositing_kernels_agree():
-    """render.cu (one pixel per thread) and render4.cu (four pixels per thread, default) implement the
+    """render.cu (one pixel per thread), render4.cu (four pixels per thread; chosen automatically on large images) implement the
     same compositing rules: both meet the oracle bars on every bin size, each is bit-reproducible
     across bin sizes, and they agree with each other far inside the tolerance."""
     from oracle import gs_oracle
@@ -356,7 +366,7 @@ def test_one_and_four_pixel_compositing_kernels_agree():
             st = _oracle(rs, sc)
             ref = gs_oracle.backward(st, w.numpy())
             per_mode = {}
-            for mode in (1, 0):
+            for mode in (1, 0):          # four pixels per thread, one pixel per thread
                 _cabi.set_option("render", mode)
                 base = None
                 for shift in (-1, 0, 2):
@@ -382,7 +392,7 @@ def test_one_and_four_pixel_compositing_kernels_agree():
         assert psnr(color, st.color) >= PSNR_MIN
         _check_grads(grads, ref, names)
     finally:
-        _cabi.set_option("render", 1)
+        _cabi.set_option("render", -1)
         _cabi.set_option("bin_shift", -1)
 
 

@@ -58,13 +58,15 @@ def test_gs_loss_matches_torch_and_scales_upstream():
     from robosimgs_b200.losses import gs_loss
     dev = torch.device("cuda:0")
     g = torch.Generator().manual_seed(3)
-    a, b = torch.rand(3, 120, 200, generator=g), torch.rand(3, 120, 200, generator=g)
+    a, b = torch.rand(3, 121, 201, generator=g), torch.rand(3, 121, 201, generator=g)     # numel % 4 != 0
     x = a.to(dev).requires_grad_(True)
-    (3.0 * gs_loss(x, b.to(dev), 0.2)).backward()
+    val = 3.0 * gs_loss(x, b.to(dev), 0.2)
+    val.backward()
     xr = a.double().to(dev).requires_grad_(True)
     bd = b.double().to(dev)
     ref = 3.0 * (0.8 * (xr - bd).abs().mean() + 0.2 * (1.0 - _torch_ssim(xr, bd)))
     ref.backward()
+    assert abs(float(val) - float(ref)) < 1e-5
     err = float((x.grad.double() - xr.grad).abs().max() / xr.grad.abs().max())
     assert err < 1e-4, err
 

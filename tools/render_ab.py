@@ -53,6 +53,6 @@ for label, om in (("opaque", 1.0), ("sparse_x0.03", 0.03)):
         print(label, "cmp", json.dumps(cmp), flush=True)
         res["cmp"] = cmp
     out[label] = {str(k): ({kk: vv for kk, vv in v.items() if not kk.startswith("_")} if isinstance(v, dict) else v) for k, v in res.items()}
-_cabi.set_option("render", 1)
+_cabi.set_option("render", -1)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/render_ab.json", "w"), indent=1)

@@ -1,17 +1,45 @@
-"""Small fwd+bwd cases for compute-sanitizer (memcheck / racecheck / synccheck)."""
+"""Small fwd+bwd cases for compute-sanitizer (memcheck / racecheck / synccheck): both compositing kernel
+families, both record-gather modes, both binning pipelines, library sort with 32- and 64-bit keys (tie
+repair incl. long runs), cooperative sort, bin shifts auto/0/2, long lists crossing ring stages, ragged image,
+fused SSIM / Adam / photometric loss."""
 import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 from helpers import small_scene, gpu_render
 from robosimgs_b200 import _cabi
-for gather in (1, 0):
-    _cabi.set_option("gather", gather)
-    for (P, W, H, deg, shift) in ((3000, 200, 136, 3, -1), (6000, 64, 48, 0, 0), (500, 37, 23, 1, 2)):
+from robosimgs_b200.scenes import Scene
+quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
+cases = ((3000, 200, 136, 3, -1), (6000, 64, 48, 0, 0), (500, 37, 23, 1, 2))
+modes = [dict(render=1, gather=1, binning=0, sort=1, sort_keys=32), dict(render=0, gather=1, binning=0, sort=0, sort_keys=32),
+         dict(render=0, gather=0, binning=0, sort=2, sort_keys=64), dict(render=1, gather=1, binning=1, sort=1, sort_keys=32),
+         dict(render=1, gather=1, binning=0, sort=0, sort_keys=64)]
+if quick:
+    modes, cases = modes[:2] + modes[3:4], cases[:2]
+for m in modes:
+    for k, v in m.items():
+        _cabi.set_option(k, v)
+    for (P, W, H, deg, shift) in cases:
         _cabi.set_option("bin_shift", shift)
         sc, cam, rs = small_scene(P=P, degree=deg, W=W, H=H)
         if P == 6000:
             sc.opacities.mul_(0.15)
         w = torch.rand(3, H, W)
         color, radii, grads = gpu_render(sc, cam, deg, bg=(0.2, 0.1, 0.4), grad_weight=w)
-        print("ok", gather, P, W, H, float(color.mean()), flush=True)
+        print("ok", m, P, W, H, float(color.mean()), flush=True)
+    # equal depths: long tie runs
+    sc, cam, rs = small_scene(P=1500, degree=0, W=96, H=64, eye=(0.0, 0.0, 3.0))
+    flat = Scene(sc.means3D * torch.tensor([1.0, 1.0, 0.0]), sc.shs, sc.opacities, sc.scales, sc.rotations, 0)
+    _cabi.set_option("bin_shift", -1)
+    color, _, _ = gpu_render(flat, cam, 0, bg=(0.2, 0.1, 0.4), grad_weight=torch.rand(3, 64, 96))
+    print("ok ties", m, float(color.mean()), flush=True)
+for k, v in dict(render=-1, gather=1, binning=-1, sort=1, sort_keys=32, bin_shift=-1).items():
+    _cabi.set_option(k, v)
+from robosimgs_b200.losses import gs_loss
+from robosimgs_b200.optim import FusedAdam
+dev = torch.device("cuda:0")
+x = torch.rand(3, 45, 70, device=dev, requires_grad=True)
+gs_loss(x, torch.rand(3, 45, 70, device=dev)).backward()
+opt = FusedAdam([x], lr=1e-2); opt.step()
+torch.cuda.synchronize()
+print("ok train neighbours", float(x.mean()))
