@@ -117,7 +117,7 @@ class SceneRenderer:
     _tags = 0
 
     def __init__(self, scene: dict, sh_degree: int, bg: torch.Tensor, height: int, width: int, streams: int = 2,
-                 graphs: bool = True):
+                 graphs: bool = True, host_frames: bool = True):
         from . import rasterizer
         self.rz = rasterizer
         self.scene, self.deg, self.H, self.W = scene, int(sh_degree), int(height), int(width)
@@ -125,6 +125,7 @@ class SceneRenderer:
         self.bg = bg.to(self.dev)
         self.means2D = torch.zeros_like(scene["means3D"])
         self.graphs = bool(graphs)
+        self.host_frames = bool(host_frames)     # False: frames stay on the device (collect() returns fp32 [3,H,W])
         self.capacity = 0
         self.redone = 0
         self.fs = FrameStreams(self.dev, streams)
@@ -134,8 +135,9 @@ class SceneRenderer:
             self.slots.append(dict(
                 stream=self.fs.streams[i % len(self.fs.streams)], tag=("scene-renderer", SceneRenderer._tags),
                 cam_host=torch.zeros(35, dtype=torch.float32).pin_memory(), cam_dev=torch.zeros(35, device=self.dev),
-                frame_host=torch.empty((self.H, self.W, 3), dtype=torch.uint8).pin_memory(),
-                rgb8=torch.empty((self.H, self.W, 3), dtype=torch.uint8, device=self.dev),
+                frame_host=torch.empty((self.H, self.W, 3), dtype=torch.uint8).pin_memory() if host_frames else None,
+                rgb8=torch.empty((self.H, self.W, 3), dtype=torch.uint8, device=self.dev) if host_frames else None,
+                color=None,
                 word=torch.zeros(1, dtype=torch.int32).pin_memory(), event=torch.cuda.Event(),
                 graph=None, graph_capacity=0, ticket=None, busy=False, cam=None))
         self.n = 0
@@ -143,8 +145,7 @@ class SceneRenderer:
     # -- one frame on the current stream -------------------------------------------------------------
     def _enqueue(self, slot, tanfovx, tanfovy, exact: bool, in_capture: bool):
         rz = self.rz
-        d = slot["cam_dev"]
-        d.copy_(slot["cam_host"], non_blocking=True)
+        d = slot["cam_dev"]          # filled by submit() (outside any captured graph)
         rs = rz.GaussianRasterizationSettings(self.H, self.W, tanfovx, tanfovy, self.bg, 1.0, d[0:16].view(4, 4),
                                               d[16:32].view(4, 4), self.deg, d[32:35], False, False)
         sc = self.scene
@@ -158,30 +159,38 @@ class SceneRenderer:
             else:
                 opts = rz.DeferOptions(capacity=self.capacity, word=slot["word"], record_event=False)
                 color, _, ticket = r.forward_deferred(sc["means3D"], self.means2D, sc["opacities"], options=opts, **kw)
-            rz.export_rgb8(color, out=slot["rgb8"])
+            if self.host_frames:
+                rz.export_rgb8(color, out=slot["rgb8"])
         finally:
             rz.LEASE_TAG = None
-        slot["frame_host"].copy_(slot["rgb8"], non_blocking=True)
+        if self.host_frames:
+            slot["frame_host"].copy_(slot["rgb8"], non_blocking=True)
+        else:
+            slot["color"] = color    # inside a captured graph this tensor is static: replays rewrite it in place
         return ticket
 
     def _set_capacity(self, pairs: int) -> None:
         q = 1 << 16
         self.capacity = ((int(pairs * 1.0625) + 32768 + q - 1) // q) * q
 
-    def submit(self, cam: Camera) -> int:
+    def submit(self, cam: Camera, cam_block: Optional[torch.Tensor] = None) -> int:
+        """Queue one frame.  cam_block: optional DEVICE tensor of 35 floats (viewmatrix, projmatrix, campos --
+        transposed/flattened like the host block) for cameras that are already resident in HBM."""
         slot = self.slots[self.n % len(self.slots)]
         if slot["busy"]:
             raise RuntimeError("SceneRenderer: collect() the oldest frame before submitting more "
                                f"({len(self.slots)} frames may be in flight)")
         handle = self.n
         self.n += 1
-        h = slot["cam_host"]
-        h[0:16] = cam.viewmatrix.reshape(-1)
-        h[16:32] = cam.projmatrix.reshape(-1)
-        h[32:35] = cam.campos.reshape(-1)
+        if cam_block is None:
+            h = slot["cam_host"]
+            h[0:16] = cam.viewmatrix.reshape(-1)
+            h[16:32] = cam.projmatrix.reshape(-1)
+            h[32:35] = cam.campos.reshape(-1)
         slot["cam"], slot["busy"] = cam, True
         tf = (float(cam.tanfovx), float(cam.tanfovy))
         with torch.no_grad(), torch.cuda.stream(slot["stream"]):
+            slot["cam_dev"].copy_(slot["cam_host"] if cam_block is None else cam_block, non_blocking=True)
             if self.capacity <= 0:                       # first frame: exact path, learn the pair count
                 self._enqueue(slot, *tf, exact=True, in_capture=False)
                 slot["ticket"] = None
@@ -192,7 +201,8 @@ class SceneRenderer:
                     self._enqueue(slot, *tf, exact=False, in_capture=False)       # sizes this slot's private scratch
                     slot["stream"].synchronize()
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g, stream=slot["stream"]):
+                    # thread_local: other threads (e.g. the NCCL watchdog of a multi-GPU sweep) may keep calling CUDA
+                    with torch.cuda.graph(g, stream=slot["stream"], capture_error_mode="thread_local"):
                         self._enqueue(slot, *tf, exact=False, in_capture=True)
                     slot["graph"], slot["graph_capacity"], slot["tf"] = g, self.capacity, tf
                 slot["graph"].replay()
@@ -217,7 +227,7 @@ class SceneRenderer:
                 slot["event"].record(slot["stream"])
             slot["event"].synchronize()
         slot["busy"] = False
-        return slot["frame_host"]
+        return slot["frame_host"] if self.host_frames else slot["color"]
 
     def in_flight_limit(self) -> int:
         return len(self.slots)
