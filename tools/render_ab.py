@@ -12,13 +12,14 @@ rs = settings_from_camera(cam, 3, device=dev)
 target = room_target().to(dev)
 out = {}
 modes = [int(m) for m in (sys.argv[1].split(",") if len(sys.argv) > 1 else ("0", "1"))]
-for label, om in (("opaque", 1.0), ("sparse_x0.03", 0.03)):
+for label, om, sm in (("opaque", 1.0, 1.0), ("sparse_x0.03", 0.03, 1.0), ("small_splats_x0.25", 1.0, 0.25)):
     res = {}
     for mode in modes:
         _cabi.set_option("render", mode)
         leaves = {k: getattr(sc, k).to(dev).clone().requires_grad_(True) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
         with torch.no_grad():
             leaves["opacities"].mul_(om)
+            leaves["scales"].mul_(sm)
         m2d = torch.zeros_like(leaves["means3D"], requires_grad=True)
         r = GaussianRasterizer(rs)
         fwd = lambda: r(leaves["means3D"], m2d, leaves["opacities"], shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"])
