@@ -47,6 +47,7 @@ extern "C" {
  * device->host copy of the camera.
  */
 #define B200GS_DEFER_PAIR_CHECK 1
+#define B200GS_BIN_SHIFT_HINT(s) (((s) + 1) << 8)
 
 typedef struct B200GSParams {
   int32_t P;              /* number of Gaussians */
@@ -64,7 +65,10 @@ typedef struct B200GSParams {
                              all -- *num_rendered must then point to PINNED host memory, receives D
                              asynchronously on `stream`, and the CALLER checks D <= pair_capacity_hint once the
                              stream has passed the call (a frame that fails the check is incomplete and must be
-                             rendered again).  Lets a sweep keep many independent frames in flight. */
+                             rendered again).  Lets a sweep keep many independent frames in flight.
+                             bits 8..11 (B200GS_BIN_SHIFT_HINT(s) = (s + 1) << 8, 0 = none): pairs are binned per
+                             (16 << s)^2 pixels for this call instead of the automatic choice -- a performance hint
+                             (results are identical for every bin size); b200gs_backward must get the same bits. */
   int64_t pair_capacity_hint; /* 0: size the binning buffer exactly (host waits for D before
                                  launching the binning stage, as the replaced interface does).
                                  >0: launch the whole frame for this many (Gaussian,tile) pair

@@ -84,7 +84,7 @@ static bool use_bucketed() {
   return m == 1;
 }
 
-static int bin_shift_for(int gx, int gy) {
+static int bin_shift_for(int gx, int gy, int flags = 0) {
   int forced = g_bin_shift_override.load();
   if (forced == -2) {
     const char* e = getenv("B200GS_BIN_SHIFT");
@@ -93,6 +93,14 @@ static int bin_shift_for(int gx, int gy) {
     g_bin_shift_override.store(forced);
   }
   if (forced >= 0) return forced;
+  // per-call hint (B200GSParams.flags bits 8..11 = shift + 1): the caller tracks the splat extent of its
+  // scene/view and asks for bins of a few splat extents; clamped so that bin ids stay below 65535
+  const int hinted = ((flags >> 8) & 15) - 1;
+  if (hinted >= 0) {
+    int s = hinted > 5 ? 5 : hinted;
+    while (s < 5 && (((gx + (1 << s) - 1) >> s) * ((gy + (1 << s) - 1) >> s)) >= 65535) s++;
+    return s;
+  }
   if (use_bucketed()) {
     // no key-width constraint: 64-px bins (shorter per-tile walks than 128 px, ~1.5x the pairs), coarser
     // only to keep the single-CTA bin scan short on very large images
@@ -360,7 +368,7 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int P = prm->P, H = prm->image_height, W = prm->image_width;
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
-  const int bs = bin_shift_for(gx, gy);
+  const int bs = bin_shift_for(gx, gy, prm->flags);
   const int gbx = (gx + (1 << bs) - 1) >> bs, gby = (gy + (1 << bs) - 1) >> bs;
   const int num_tiles = gbx * gby;   // bins
   const int tile_bits = tile_bits_for(num_tiles);
@@ -585,7 +593,7 @@ int b200gs_backward(const B200GSParams* prm, const float* bg, const float* viewm
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
-  const int bs = bin_shift_for(gx, gy);
+  const int bs = bin_shift_for(gx, gy, prm->flags);    // must be the flags of the forward call
   const int gbx = (gx + (1 << bs) - 1) >> bs, gby = (gy + (1 << bs) - 1) >> bs;
   const int tile_bits = tile_bits_for(gbx * gby);
   GeomBuf gb = carve_geom(const_cast<char*>(geom), P, nullptr);

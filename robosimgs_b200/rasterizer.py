@@ -157,6 +157,46 @@ def _params(P, M, rs: GaussianRasterizationSettings, hint: int = 0, near_plane: 
                               int(bool(rs.prefiltered)), int(bool(rs.debug)), float(near_plane), int(flags), int(hint))
 
 
+# Bin-size policy (B200GSParams.flags bits 8..11).  The library's automatic bin size only looks at the image
+# (largest bins that keep the sort key narrow: 128 px at 1080p) -- right for scenes of large splats, but with
+# small splats a tile then walks thousands of records of its bin to find the few that touch it.  On the first
+# frame of a (device, P, H, W) the pairs-per-touching-Gaussian ratio D / #(radii > 0) ~ (1 + extent/bin)^2 gives
+# the typical splat extent on screen; later frames ask for bins of about three extents (32..256 px).  Results
+# do not depend on the bin size.  One reduction + sync on that first frame, re-checked every 256 synchronous calls.
+_BIN_POLICY: dict = {}
+ADAPT_BIN_SIZE = True
+
+
+def _default_bin_shift(H: int, W: int) -> int:
+    gx, gy = (W + 15) // 16, (H + 15) // 16
+    s = 0
+    while s < 3 and ((gx + (1 << s) - 1) >> s) * ((gy + (1 << s) - 1) >> s) > 255:
+        s += 1
+    return s
+
+
+def _bin_flags(hint_key, H, W):
+    pol = _BIN_POLICY.setdefault(hint_key, {"shift": -1, "calls": 0})
+    used = pol["shift"] if pol["shift"] >= 0 else _default_bin_shift(H, W)
+    return pol, used, ((pol["shift"] + 1) << 8 if pol["shift"] >= 0 else 0)
+
+
+def _adapt_bin_size(pol, used, hint_key, D, radii):
+    pol["calls"] += 1
+    if not ADAPT_BIN_SIZE or D <= 0 or not (pol["calls"] == 1 or pol["calls"] % 256 == 0):
+        return
+    import math
+    touch = int((radii > 0).sum())
+    if touch <= 0:
+        return
+    b = 16 << used
+    extent = max(math.sqrt(max(D / touch, 1.0)) - 1.0, 0.0) * b
+    new = min(4, max(1, int(round(math.log2(max(3.0 * extent, 16.0) / 16.0)))))
+    if new != used:
+        pol["shift"] = new
+        _PAIR_HINTS.pop(hint_key, None)          # the pair count changes with the bin size
+
+
 class PairTicket:
     """Receipt of a forward call made with the pair-count check DEFERRED (forward-only sweeps).
 
@@ -243,7 +283,8 @@ class _RasterizeGaussians(torch.autograd.Function):
             ticket = PairTicket(hint if P > 0 else 0, hint_key, opts.word)
             ticket_box.append(ticket)
         defer = ticket is not None and hint > 0 and P > 0
-        prm = _params(P, M, rs, hint, near_plane, _cabi.DEFER_PAIR_CHECK if defer else 0)
+        pol, shift_used, bin_flags = _bin_flags(hint_key, H, W)
+        prm = _params(P, M, rs, hint, near_plane, (_cabi.DEFER_PAIR_CHECK if defer else 0) | bin_flags)
         color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
         radii = torch.empty((P,), dtype=torch.int32, device=dev)
         num_rendered = C.c_int32(0)
@@ -271,8 +312,11 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.raster_settings = rs
         ctx.near_plane = near_plane
         ctx.num_rendered = int(num_rendered.value)
+        ctx.bin_flags = bin_flags
         if not defer:
             _PAIR_HINTS[hint_key] = max(ctx.num_rendered, int(last_D * 0.97))
+            if not rs.debug:
+                _adapt_bin_size(pol, shift_used, hint_key, ctx.num_rendered, radii)
         ctx.M = M
         ctx.present = (sh is not None, colors_precomp is not None, scales is not None,
                        cov3Ds_precomp is not None)
@@ -313,7 +357,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         g_scales = e(P, 3) if has_sr else None
         g_rots = e(P, 4) if has_sr else None
         g_cov = e(P, 6) if has_cov else None
-        prm = _params(P, ctx.M, rs, 0, ctx.near_plane)
+        prm = _params(P, ctx.M, rs, 0, ctx.near_plane, ctx.bin_flags)
         with torch.cuda.device(dev):
             lease = _Lease(dev, ("scratch",))
             stream = C.c_void_p(lease.stream)

@@ -170,6 +170,9 @@ class SceneRenderer:
         return ticket
 
     def _set_capacity(self, pairs: int) -> None:
+        if pairs <= 0:                 # no pair count known (yet / any more): next frame takes the exact path
+            self.capacity = 0
+            return
         q = 1 << 16
         self.capacity = ((int(pairs * 1.0625) + 32768 + q - 1) // q) * q
 

@@ -217,16 +217,20 @@ def test_speculative_pair_capacity_paths_are_bit_identical():
     kw = dict(shs=sc.shs.to(dev), scales=sc.scales.to(dev), rotations=sc.rotations.to(dev))
     key = (dev.index, 4000, 240, 320)
     outs = []
-    for hint in (0, 10_000_000, 17):
-        rasterizer._PAIR_HINTS.pop(key, None)
-        if hint:
-            rasterizer._PAIR_HINTS[key] = hint
-        color, radii = GaussianRasterizer(rs_gpu)(*args, **kw)
-        outs.append((color.detach().cpu().numpy(), color.grad_fn.num_rendered))
-        assert rasterizer._PAIR_HINTS[key] >= color.grad_fn.num_rendered
-        w = torch.ones_like(color)
-        (color * w).sum().backward()                       # backward works from every path
-        assert torch.isfinite(args[0].grad).all()
+    rasterizer.ADAPT_BIN_SIZE = False                       # keep the bin size (and so the pair count) fixed
+    try:
+        for hint in (0, 10_000_000, 17):
+            rasterizer._PAIR_HINTS.pop(key, None)
+            if hint:
+                rasterizer._PAIR_HINTS[key] = hint
+            color, radii = GaussianRasterizer(rs_gpu)(*args, **kw)
+            outs.append((color.detach().cpu().numpy(), color.grad_fn.num_rendered))
+            assert rasterizer._PAIR_HINTS[key] >= color.grad_fn.num_rendered
+            w = torch.ones_like(color)
+            (color * w).sum().backward()                       # backward works from every path
+            assert torch.isfinite(args[0].grad).all()
+    finally:
+        rasterizer.ADAPT_BIN_SIZE = True
     assert outs[0][1] == outs[1][1] == outs[2][1] > 17
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][0], outs[2][0])
 
@@ -244,6 +248,7 @@ def test_deferred_pair_check_ticket_protocol():
     kw = dict(shs=t["shs"], scales=t["scales"], rotations=t["rotations"])
     try:
         _cabi.set_option("bin_shift", 0)
+        rasterizer.ADAPT_BIN_SIZE = False
         with torch.no_grad():
             r = GaussianRasterizer(rs)
             rasterizer._PAIR_HINTS.clear()
@@ -265,6 +270,41 @@ def test_deferred_pair_check_ticket_protocol():
             assert t3.ok() and torch.equal(c3, ref)
     finally:
         _cabi.set_option("bin_shift", -1)
+        rasterizer.ADAPT_BIN_SIZE = True
+
+
+def test_bin_size_policy_follows_the_splat_extent_and_never_changes_results():
+    """The Python layer asks for bins of about three splat extents (per-call flags bits 8..11): small splats
+    -> finer bins than the image-only default, large splats -> the default or coarser; images, radii and
+    gradients are the same either way (the bin size is a pure performance knob)."""
+    from robosimgs_b200 import rasterizer
+    from robosimgs_b200.scenes import Scene
+    W, H = 640, 480                                         # image-only default: 64-px bins (shift 2)
+    assert rasterizer._default_bin_shift(H, W) == 2
+    w = torch.rand(3, H, W, generator=torch.Generator().manual_seed(31))
+    key = (0, 5000, H, W)
+    picked = {}
+    for label, mul in (("small", 0.2), ("large", 3.0)):
+        sc, cam, rs = small_scene(P=5000, degree=1, W=W, H=H, big=0)
+        sc = Scene(sc.means3D, sc.shs, sc.opacities, sc.scales * mul, sc.rotations, 1)
+        results = []
+        for adapt in (False, True):
+            rasterizer.ADAPT_BIN_SIZE = adapt
+            rasterizer._BIN_POLICY.pop(key, None)
+            rasterizer._PAIR_HINTS.pop(key, None)
+            try:
+                gpu_render(sc, cam, 1, bg=(0.2, 0.1, 0.4))                      # first frame: the policy looks at it
+                results.append(gpu_render(sc, cam, 1, bg=(0.2, 0.1, 0.4), grad_weight=w))
+            finally:
+                rasterizer.ADAPT_BIN_SIZE = True
+        picked[label] = rasterizer._BIN_POLICY[key]["shift"]
+        (c0, r0, g0), (c1, r1, g1) = results
+        assert np.array_equal(c0, c1) and np.array_equal(r0, r1)
+        for k in ("means3D", "shs", "opacities", "scales", "rotations"):
+            assert max_rel_err(g1[k], g0[k]) < 1e-5, (label, k)
+    assert picked["small"] == 1                             # finer than the default
+    assert picked["large"] in (-1, 2, 3, 4)                 # default kept (or coarser)
+    rasterizer._BIN_POLICY.pop(key, None)
 
 
 def test_export_rgb8_matches_numpy():

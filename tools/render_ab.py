@@ -15,6 +15,8 @@ modes = [int(m) for m in (sys.argv[1].split(",") if len(sys.argv) > 1 else ("0",
 for label, om, sm in (("opaque", 1.0, 1.0), ("sparse_x0.03", 0.03, 1.0), ("small_splats_x0.25", 1.0, 0.25)):
     res = {}
     for mode in modes:
+        from robosimgs_b200 import rasterizer as _rz
+        _rz._BIN_POLICY.clear(); _rz._PAIR_HINTS.clear()      # a fresh scene: let the bin-size policy look at it
         _cabi.set_option("render", mode)
         leaves = {k: getattr(sc, k).to(dev).clone().requires_grad_(True) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
         with torch.no_grad():
