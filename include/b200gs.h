@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define B200GS_VERSION 100
+#define B200GS_VERSION 101
 
 /* Error codes (0 = success).  b200gs_last_error() returns the message for the calling thread. */
 #define B200GS_OK 0
