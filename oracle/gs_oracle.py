@@ -14,6 +14,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import subprocess
+import sys
 from types import SimpleNamespace
 
 import numpy as np
@@ -27,7 +28,7 @@ def build(force: bool = False) -> str:
     """Compile oracle/gs_oracle.c with the committed Makefile (gcc, OpenMP)."""
     src_m = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("gs_oracle.c", "gs_oracle_impl.h", "Makefile"))
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < src_m:
-        subprocess.check_call(["make", "-C", _HERE, "-s"])
+        subprocess.check_call(["make", "-C", _HERE, "-s"], stdout=sys.stderr)
     return _SO
 
 
