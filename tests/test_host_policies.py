@@ -1,0 +1,53 @@
+"""Host-side logic of the operator layer that needs no GPU: bin-size policy, pair tickets, defer options."""
+import torch
+
+from robosimgs_b200 import rasterizer as rz
+
+
+def test_default_bin_shift_matches_the_library_rule():
+    # smallest shift with at most 255 bins, capped at 3 (api.cu:bin_shift_for, global-sort path)
+    assert rz._default_bin_shift(1080, 1920) == 3
+    assert rz._default_bin_shift(800, 800) == 2
+    assert rz._default_bin_shift(480, 640) == 2
+    assert rz._default_bin_shift(256, 256) == 1
+    assert rz._default_bin_shift(64, 64) == 0
+    assert rz._default_bin_shift(4320, 7680) == 3
+
+
+def test_bin_size_policy_tracks_the_splat_extent():
+    key = ("cpu-test", 1000, 1080, 1920)
+    rz._BIN_POLICY.pop(key, None)
+    rz._PAIR_HINTS[key] = 123
+    pol, used, flags = rz._bin_flags(key, 1080, 1920)
+    assert used == 3 and flags == 0 and pol["shift"] == -1
+    radii = torch.zeros(1000, dtype=torch.int32)
+    radii[:400] = 5
+    # C3-like: 2.08 pairs per touching Gaussian at 128-px bins -> extent ~57 px -> bins of ~170 px -> keep 128
+    rz._adapt_bin_size(pol, used, key, int(2.08 * 400), radii)
+    assert pol["shift"] == -1 and rz._PAIR_HINTS.get(key) == 123
+    # small splats: 1.16 pairs per touching Gaussian -> extent ~10 px -> 32-px bins; pair hint dropped
+    pol["calls"] = 0
+    rz._adapt_bin_size(pol, used, key, int(1.16 * 400), radii)
+    assert pol["shift"] == 1 and key not in rz._PAIR_HINTS
+    pol2, used2, flags2 = rz._bin_flags(key, 1080, 1920)
+    assert used2 == 1 and flags2 == (2 << 8)
+    # only the first call (and every 256th) looks; in between nothing changes
+    rz._adapt_bin_size(pol2, used2, key, 4 * 400, radii)
+    assert pol2["shift"] == 1 and pol2["calls"] == 2
+    rz._BIN_POLICY.pop(key, None)
+
+
+def test_pair_ticket_and_defer_options():
+    key = ("cpu-test", 10, 8, 8)
+    word = torch.zeros(1, dtype=torch.int32)
+    rz._PAIR_HINTS.pop(key, None)
+    t = rz.PairTicket(1000, key, word)
+    word[0] = 900
+    assert t.ok() and t.pairs == 900 and rz._PAIR_HINTS[key] == 900
+    assert t.ok()                                   # idempotent
+    t2 = rz.PairTicket(1000, key, word)
+    word[0] = 5000
+    assert not t2.ok() and rz._PAIR_HINTS[key] == 5000      # the hint recovers from an overflow
+    opts = rz.DeferOptions(capacity=4096, word=word, record_event=False)
+    assert opts.capacity == 4096 and opts.word is word and not opts.record_event and len(opts) == 0
+    rz._PAIR_HINTS.pop(key, None)
