@@ -5,7 +5,7 @@
 // gso_render_backward), re-shaped around the measured bound of those kernels: FP32 issue
 // (86 % issue-active, 0.7 % of HBM peak -- profiles/r1_ncu_full_summary_d.csv).  On the opaque C3
 // frame a tile walks only ~75 records of its bin list and ~56 of them touch the tile, nearly all of
-// them covering every pixel of the block that evaluates them (tools/sim/run_sim.py), so three
+// them covering every pixel of the block that evaluates them (tests/devtools/sim/run_sim.py), so three
 // quarters of the issue slots of the one-pixel-per-thread kernel are the per-record loop itself
 // (mask bookkeeping, three shared-memory broadcasts, dy/conic products that are identical for the
 // pixels of a row) -- work that does not grow with the number of pixels a thread owns.

@@ -1,8 +1,9 @@
 """Runs every BASELINE.json config on one GPU and writes gpurun_out/configs_r1.json
 (GPU ms, Mpix/s, pair counts; PSNR / gradient error against the oracle where the CPU oracle is
-affordable).  Dev/documentation tool -- bench.py is the contract benchmark."""
+affordable).  Dev/documentation tool -- bench.py is the contract benchmark.  Lives under tests/ because it uses
+the oracle as its checker (only tests/, smoke() and bench.py's CPU arms may touch oracle/)."""
 import json, os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 from robosimgs_b200 import GaussianRasterizer, _cabi, compositor as cp, export_rgb8

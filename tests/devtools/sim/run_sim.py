@@ -1,7 +1,7 @@
-"""Work model of the compositing kernels on C3 (analysis only): python tools/sim/run_sim.py [P] [W] [H] [opacity_scale]"""
+"""Work model of the compositing kernels on C3 (analysis only): python tests/devtools/sim/run_sim.py [P] [W] [H] [opacity_scale]"""
 import ctypes as C, os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "..", ".."))
 import torch
 from oracle import gs_oracle
 from robosimgs_b200.scenes import room_scene, settings_from_camera

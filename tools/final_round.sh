@@ -13,4 +13,4 @@ timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/f
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/final_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/final_launches_bench.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:"k_render|k_project|k_emit|k_tile_ranges|k_fix|Onesweep|k_photometric" -s 22 -c 22 -o gpurun_out/final_prof python tools/ncu_target.py 3 > gpurun_out/final_ncu.log 2>&1; tail -1 gpurun_out/final_ncu.log
 timeout 300 python tools/compare_naive.py > gpurun_out/final_naive.log 2>&1; tail -c 400 gpurun_out/final_naive.log
-timeout 400 python tools/run_configs.py > gpurun_out/final_configs.log 2>&1; tail -3 gpurun_out/final_configs.log
+timeout 400 python tests/devtools/run_configs.py > gpurun_out/final_configs.log 2>&1; tail -3 gpurun_out/final_configs.log
