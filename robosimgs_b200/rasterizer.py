@@ -181,7 +181,8 @@ def _bin_flags(hint_key, H, W):
     return pol, used, ((pol["shift"] + 1) << 8 if pol["shift"] >= 0 else 0)
 
 
-def _adapt_bin_size(pol, used, hint_key, D, radii):
+def _adapt_bin_size(pol, used, hint_key, D, radii, coverage=None):
+    """coverage: callable returning the mean of (1 - final transmittance) over the frame, or None."""
     pol["calls"] += 1
     if not ADAPT_BIN_SIZE or D <= 0 or not (pol["calls"] == 1 or pol["calls"] % 256 == 0):
         return
@@ -192,6 +193,11 @@ def _adapt_bin_size(pol, used, hint_key, D, radii):
     b = 16 << used
     extent = max(math.sqrt(max(D / touch, 1.0)) - 1.0, 0.0) * b
     new = min(4, max(1, int(round(math.log2(max(3.0 * extent, 16.0) / 16.0)))))
+    # large splats AND a frame that saturates everywhere: tiles stop after the first few records of their
+    # list, so one size coarser costs the compositing kernels nothing and makes emission and sort lighter
+    # (C3: 0.372 -> 0.356 ms); a frame that does not saturate walks its whole lists and must not go coarser
+    if new == 3 and coverage is not None and coverage() > 0.995:
+        new = 4
     if new != used:
         pol["shift"] = new
         _PAIR_HINTS.pop(hint_key, None)          # the pair count changes with the bin size
@@ -316,7 +322,13 @@ class _RasterizeGaussians(torch.autograd.Function):
         if not defer:
             _PAIR_HINTS[hint_key] = max(ctx.num_rendered, int(last_D * 0.97))
             if not rs.debug:
-                _adapt_bin_size(pol, shift_used, hint_key, ctx.num_rendered, radii)
+                def coverage():
+                    a = torch.empty((H, W), dtype=torch.float32, device=dev)
+                    with torch.cuda.device(dev):
+                        _cabi.check(L.b200gs_extract_alpha(_ptr(lease.tensor("img")), C.c_int32(H), C.c_int32(W),
+                                                           _ptr(a), stream))
+                    return float(a.mean())
+                _adapt_bin_size(pol, shift_used, hint_key, ctx.num_rendered, radii, coverage)
         ctx.M = M
         ctx.present = (sh is not None, colors_precomp is not None, scales is not None,
                        cov3Ds_precomp is not None)

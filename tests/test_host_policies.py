@@ -23,8 +23,14 @@ def test_bin_size_policy_tracks_the_splat_extent():
     radii = torch.zeros(1000, dtype=torch.int32)
     radii[:400] = 5
     # C3-like: 2.08 pairs per touching Gaussian at 128-px bins -> extent ~57 px -> bins of ~170 px -> keep 128
-    rz._adapt_bin_size(pol, used, key, int(2.08 * 400), radii)
+    rz._adapt_bin_size(pol, used, key, int(2.08 * 400), radii, lambda: 0.9)
     assert pol["shift"] == -1 and rz._PAIR_HINTS.get(key) == 123
+    # ... and one size coarser when the frame saturates everywhere
+    pol["calls"] = 0
+    rz._adapt_bin_size(pol, used, key, int(2.08 * 400), radii, lambda: 0.9999)
+    assert pol["shift"] == 4 and key not in rz._PAIR_HINTS
+    pol["shift"], pol["calls"] = -1, 0
+    rz._PAIR_HINTS[key] = 123
     # small splats: 1.16 pairs per touching Gaussian -> extent ~10 px -> 32-px bins; pair hint dropped
     pol["calls"] = 0
     rz._adapt_bin_size(pol, used, key, int(1.16 * 400), radii)
