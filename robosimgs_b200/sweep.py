@@ -169,12 +169,15 @@ class SceneRenderer:
             slot["color"] = color    # inside a captured graph this tensor is static: replays rewrite it in place
         return ticket
 
-    def _set_capacity(self, pairs: int) -> None:
+    def _set_capacity(self, pairs: int, grow_only: bool = False) -> None:
         if pairs <= 0:                 # no pair count known (yet / any more): next frame takes the exact path
             self.capacity = 0
             return
         q = 1 << 16
-        self.capacity = ((int(pairs * 1.0625) + 32768 + q - 1) // q) * q
+        need = ((int(pairs * 1.0625) + 32768 + q - 1) // q) * q
+        # grow_only: a frame that overflowed may have been submitted under an OLDER, smaller capacity than the
+        # current one (several frames are in flight); its pair count must never shrink the capacity again
+        self.capacity = max(self.capacity, need) if grow_only else need
 
     def submit(self, cam: Camera, cam_block: Optional[torch.Tensor] = None) -> int:
         """Queue one frame.  cam_block: optional DEVICE tensor of 35 floats (viewmatrix, projmatrix, campos --
@@ -224,7 +227,7 @@ class SceneRenderer:
             # pair capacity exceeded (abrupt view change): render this frame again, exactly; later
             # frames use (and graphs are re-captured for) the larger capacity
             self.redone += 1
-            self._set_capacity(t.pairs)
+            self._set_capacity(t.pairs, grow_only=True)
             with torch.no_grad(), torch.cuda.stream(slot["stream"]):
                 self._enqueue(slot, float(slot["cam"].tanfovx), float(slot["cam"].tanfovy), exact=True, in_capture=False)
                 slot["event"].record(slot["stream"])

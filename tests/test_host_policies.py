@@ -57,3 +57,21 @@ def test_pair_ticket_and_defer_options():
     opts = rz.DeferOptions(capacity=4096, word=word, record_event=False)
     assert opts.capacity == 4096 and opts.word is word and not opts.record_event and len(opts) == 0
     rz._PAIR_HINTS.pop(key, None)
+
+
+def test_scene_renderer_capacity_never_shrinks_on_overflow():
+    """Frames in flight were submitted under different capacities: an overflow report from an older frame
+    (small pair count, small old capacity) must not undo the growth a later frame already caused."""
+    from robosimgs_b200.sweep import SceneRenderer
+    r = SceneRenderer.__new__(SceneRenderer)          # capacity logic only: no device needed
+    r.capacity = 0
+    r._set_capacity(3_000_000)
+    c3 = r.capacity
+    assert c3 >= 3_000_000 and c3 % 65536 == 0
+    r._set_capacity(5_000_000, grow_only=True)
+    c5 = r.capacity
+    assert c5 > c3
+    r._set_capacity(3_200_000, grow_only=True)        # stale overflow report from an older frame
+    assert r.capacity == c5
+    r._set_capacity(0)
+    assert r.capacity == 0
