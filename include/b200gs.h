@@ -219,6 +219,16 @@ int b200gs_adam_step(const B200GSAdamGroup* groups, int32_t num_groups, float be
 int b200gs_buffer_sizes(int32_t P, int32_t image_height, int32_t image_width, int64_t D,
                         size_t* geom_bytes, size_t* binning_bytes, size_t* img_bytes);
 
+/* Byte offsets of the per-Gaussian arrays inside the geom buffer of a forward call with P Gaussians -- lets a
+ * test or a debugger compare the projection stage field by field without the library
+ * exposing its scratch as API.  offsets[0] rec: float[P][12] = {x, y, conic A, B | C, opacity, threshold,
+ * index bits | r, g, b, radius}, written only for Gaussians that touch a bin; [1] depth_key: uint32[P] IEEE bits
+ * of the view-space depth (0xFFFFFFFF = culled); [2] tiles: uint32[P] bins touched; [3] offsets: uint32[P]
+ * inclusive scan of tiles (global-sort pipeline only); [4] clamped: uint8[P], bit c = colour channel c was
+ * clamped at 0. */
+#define B200GS_GEOM_FIELDS 5
+int b200gs_geom_layout(int32_t P, size_t offsets[B200GS_GEOM_FIELDS]);
+
 /* Message of the last error raised on the calling thread ("" if none). */
 const char* b200gs_last_error(void);
 

@@ -17,7 +17,7 @@ EXPORTED_SYMBOLS = (
     "b200gs_profile_enable", "b200gs_profile_read", "b200gs_stage_name", "b200gs_export_rgb8",
     "b200gs_set_option", "b200gs_ply_activate", "b200gs_transform_gaussians",
     "b200gs_extract_alpha", "b200gs_photometric_loss", "b200gs_photometric_loss_backward",
-    "b200gs_ssim_forward", "b200gs_ssim_backward", "b200gs_adam_step",
+    "b200gs_ssim_forward", "b200gs_ssim_backward", "b200gs_adam_step", "b200gs_geom_layout",
 )
 ADAM_MAX_GROUPS = 8
 DEFER_PAIR_CHECK = 1
@@ -106,6 +106,8 @@ def lib():
                                    C.c_int32, vp]
     L.b200gs_extract_alpha.restype = C.c_int
     L.b200gs_extract_alpha.argtypes = [vp, C.c_int32, C.c_int32, fp, vp]
+    L.b200gs_geom_layout.restype = C.c_int
+    L.b200gs_geom_layout.argtypes = [C.c_int32, C.POINTER(C.c_size_t)]
     L.b200gs_set_option.restype = C.c_int
     L.b200gs_set_option.argtypes = [C.c_char_p, C.c_int]
     L.b200gs_profile_enable.argtypes = [C.c_int]
@@ -141,3 +143,10 @@ def profile_read(reset: bool = True) -> dict:
 def set_option(name: str, value: int) -> None:
     """Tuning knobs of the library ("bin_shift": -1 auto / 0..5, "gather": 0 TMA / 1 LDGSTS)."""
     check(lib().b200gs_set_option(name.encode(), int(value)))
+
+
+def geom_layout(P: int) -> dict:
+    """Byte offsets of the per-Gaussian arrays inside a forward call's geom buffer (b200gs_geom_layout)."""
+    off = (C.c_size_t * 5)()
+    check(lib().b200gs_geom_layout(C.c_int32(int(P)), off))
+    return dict(zip(("rec", "depth_key", "tiles", "offsets", "clamped"), (int(o) for o in off)))

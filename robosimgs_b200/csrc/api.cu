@@ -351,6 +351,16 @@ int b200gs_buffer_sizes(int32_t P, int32_t H, int32_t W, int64_t D, size_t* geom
   return 0;
 }
 
+int b200gs_geom_layout(int32_t P, size_t offsets[B200GS_GEOM_FIELDS]) {
+  g_err[0] = 0;
+  if (P < 0 || !offsets) { set_error("geom_layout: invalid arguments"); return B200GS_ERR_INVALID_ARG; }
+  GeomBuf g = carve_geom(reinterpret_cast<char*>(uintptr_t(128)), P, nullptr);   // fake 128-aligned base
+  auto off = [](const void* p) { return (size_t)(reinterpret_cast<uintptr_t>(p) - 128); };
+  offsets[0] = off(g.rec); offsets[1] = off(g.depth_key); offsets[2] = off(g.tiles);
+  offsets[3] = off(g.offsets); offsets[4] = off(g.clamped);
+  return 0;
+}
+
 int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewmatrix,
                    const float* projmatrix, const float* campos, const float* means3D,
                    const float* shs, const float* colors_precomp, const float* opacities,

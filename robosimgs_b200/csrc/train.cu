@@ -20,19 +20,9 @@ constexpr int SS_E = SS_T + 2 * SS_R;   // 26: tile + halo
 constexpr float SS_C1 = 0.01f * 0.01f;
 constexpr float SS_C2 = 0.03f * 0.03f;
 
-__constant__ float c_gauss[11];
-
-static void upload_window(cudaStream_t st) {
-  static bool done = false;   // per process; the values never change
-  if (done) return;
-  double g[11], s = 0.0;
-  for (int i = 0; i < 11; i++) { g[i] = exp(-(double)((i - 5) * (i - 5)) / (2.0 * 1.5 * 1.5)); s += g[i]; }
-  float f[11];
-  for (int i = 0; i < 11; i++) f[i] = (float)(g[i] / s);
-  cudaMemcpyToSymbolAsync(c_gauss, f, sizeof(f), 0, cudaMemcpyHostToDevice, st);
-  cudaStreamSynchronize(st);
-  done = true;
-}
+// exp(-(i-5)^2 / (2 * 1.5^2)) / sum, rounded to fp32 (the window torch builds in fp64 and casts).  Compile-time
+// constants in the kernel image: valid on every device of the process and inside stream capture.
+__device__ __constant__ float c_gauss[11] = {0.001028380123898387f, 0.0075987582094967365f, 0.036000773310661316f, 0.10936068743467331f, 0.21300554275512695f, 0.26601171493530273f, 0.21300554275512695f, 0.10936068743467331f, 0.036000773310661316f, 0.0075987582094967365f, 0.001028380123898387f};
 
 // img1 = rendered image (gradient flows to it), img2 = target.  [C][H][W].
 // Writes the three derivative maps the adjoint needs (dm/dmu1, dm/dE[x^2], dm/dE[xy]) when
@@ -164,7 +154,6 @@ __global__ void __launch_bounds__(SS_T * SS_T) k_ssim_bwd(const float* __restric
 
 void launch_ssim_fwd(const float* img1, const float* img2, int C, int H, int W, float* maps, float* out_sum,
                      cudaStream_t st) {
-  upload_window(st);
   cudaMemsetAsync(out_sum, 0, sizeof(float), st);
   const dim3 grid((W + SS_T - 1) / SS_T, (H + SS_T - 1) / SS_T, C), block(SS_T, SS_T);
   k_ssim_fwd<<<grid, block, 0, st>>>(img1, img2, H, W, maps, out_sum);
@@ -173,7 +162,6 @@ void launch_ssim_fwd(const float* img1, const float* img2, int C, int H, int W, 
 
 void launch_ssim_bwd(const float* img1, const float* img2, const float* maps, int C, int H, int W, float scale,
                      const float* upstream, float* dL_dimg1, cudaStream_t st) {
-  upload_window(st);
   const dim3 grid((W + SS_T - 1) / SS_T, (H + SS_T - 1) / SS_T, C), block(SS_T, SS_T);
   k_ssim_bwd<<<grid, block, 0, st>>>(img1, img2, maps, H, W, scale, upstream, dL_dimg1);
   count_launch();

@@ -10,8 +10,10 @@ inria-style operator this repo implements:
 
 Only what the kernels implement is accepted -- everything else raises NotImplementedError rather than
 silently rendering something different: render_mode "RGB", rasterize_mode "classic", eps2d 0.3,
-tile_size 16, pinhole cameras, no far-plane / radius clipping, 3-channel colours; ``alphas`` carry no
-gradient.
+tile_size 16, pinhole cameras, no far-plane / radius clipping, 3-channel colours.  ``meta["means2d"]`` is the
+[C, N, 2] screen-space gradient carrier (pixel units, like gsplat's) that splatfacto's densification strategy
+reads; ``alphas`` carry NO gradient (a loss term through the alpha image -- e.g. a learnt background blend --
+gets none): the kernels' adjoint covers the colour image only.
 """
 from __future__ import annotations
 
@@ -22,10 +24,14 @@ import torch
 from .rasterizer import GaussianRasterizationSettings, _RasterizeGaussians
 
 
-def _camera_matrices(viewmat: torch.Tensor, K: torch.Tensor, width: int, height: int, znear: float, zfar: float):
+def _camera_matrices(viewmat: torch.Tensor, K: torch.Tensor, K_host, width: int, height: int, znear: float,
+                     zfar: float):
+    """K_host: the same intrinsics as Python floats (fx, fy) -- tan(fov/2) is a host scalar of the C ABI, and reading
+    it from a CUDA `K` here would cost one device->host sync per camera (rasterization() fetches all cameras' Ks
+    with a single copy instead)."""
     fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
-    tanfovx = float(width / (2.0 * fx))
-    tanfovy = float(height / (2.0 * fy))
+    tanfovx = float(width / (2.0 * K_host[0]))
+    tanfovy = float(height / (2.0 * K_host[1]))
     P = torch.zeros(4, 4, dtype=viewmat.dtype, device=viewmat.device)
     P[0, 0] = 2.0 * fx / width
     P[1, 1] = 2.0 * fy / height
@@ -71,17 +77,24 @@ def rasterization(means: torch.Tensor, quats: torch.Tensor, scales: torch.Tensor
         shs, cols = colors.reshape(N, -1, 3), means.new_empty(0)
     empty = means.new_empty(0)
     outs, alphas, radii_all = [], [], []
+    K_host = Ks.detach()[:, [0, 1], [0, 1]].double().cpu().tolist()       # one copy for all cameras
+    # meta["means2d"] [C, N, 2]: gradient carrier in PIXEL units, as gsplat's densification strategies read it
+    # (info["means2d"].retain_grad() ... .grad); the kernels report the screen-space gradient NDC-scaled
+    # (x 0.5 W, x 0.5 H -- the public inria convention), so the carrier enters scaled by (2/W, 2/H).
+    means2d = torch.zeros((C_, N, 2), dtype=means.dtype, device=dev, requires_grad=torch.is_grad_enabled())
+    to_ndc = torch.tensor([2.0 / width, 2.0 / height, 0.0], dtype=means.dtype, device=dev)
     for c in range(C_):
-        view_t, proj_t, campos, tfx, tfy = _camera_matrices(viewmats[c].float(), Ks[c].float(), width, height,
+        view_t, proj_t, campos, tfx, tfy = _camera_matrices(viewmats[c].float(), Ks[c].float(), K_host[c], width, height,
                                                             max(near_plane, 1e-4), 1000.0)
         bg = backgrounds[c].float() if backgrounds is not None else torch.zeros(3, device=dev)
         rs = GaussianRasterizationSettings(int(height), int(width), tfx, tfy, bg, 1.0, view_t, proj_t,
                                            0 if sh_degree is None else int(sh_degree), campos, False, False)
-        means2D = torch.zeros_like(means, requires_grad=means.requires_grad)
-        color, radii, alpha = _RasterizeGaussians.apply(means, means2D, shs, cols, opac, scales, quats_n, empty, rs,
+        carrier = torch.nn.functional.pad(means2d[c], (0, 1)) * to_ndc
+        color, radii, alpha = _RasterizeGaussians.apply(means, carrier, shs, cols, opac, scales, quats_n, empty, rs,
                                                         torch.is_grad_enabled(), float(near_plane), True)
         outs.append(color.permute(1, 2, 0))
         alphas.append(alpha[..., None])
         radii_all.append(radii)
-    meta = {"radii": torch.stack(radii_all), "width": width, "height": height, "tile_size": 16, "n_cameras": C_}
+    meta = {"radii": torch.stack(radii_all), "means2d": means2d, "width": width, "height": height, "tile_size": 16,
+            "n_cameras": C_}
     return torch.stack(outs), torch.stack(alphas), meta

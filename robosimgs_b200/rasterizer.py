@@ -281,7 +281,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         # deferred pair check (forward-only callers that pass a ticket box): only once a hint exists
         ticket = None
         if ticket_box is not None:
-            if grad_mode and any(ctx.needs_input_grad):
+            if torch.is_grad_enabled() and any(ctx.needs_input_grad):
                 raise _cabi.B200GSError("the deferred pair check is for forward-only rendering (no_grad)")
             opts = ticket_box if isinstance(ticket_box, DeferOptions) else DeferOptions()
             if opts.capacity > 0:
@@ -330,6 +330,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                     return float(a.mean())
                 _adapt_bin_size(pol, shift_used, hint_key, ctx.num_rendered, radii, coverage)
         ctx.M = M
+        ctx.in_shapes = (None if sh is None else tuple(sh.shape), tuple(opacities.shape))
         ctx.present = (sh is not None, colors_precomp is not None, scales is not None,
                        cov3Ds_precomp is not None)
         if grad_mode and any(ctx.needs_input_grad):
@@ -383,6 +384,10 @@ class _RasterizeGaussians(torch.autograd.Function):
             lease.release()
         # order of the public interface: means3D, means2D, sh, colors_precomp, opacities, scales,
         # rotations, cov3Ds_precomp, raster_settings
+        sh_shape, opac_shape = ctx.in_shapes        # forward accepts shs [P, M*3] and opacities [P]: mirror them
+        if g_sh is not None and sh_shape is not None:
+            g_sh = g_sh.view(sh_shape)
+        g_opac = g_opac.view(opac_shape)
         return g_means3D, g_means2D, g_sh, g_col, g_opac, g_scales, g_rots, g_cov, None, None, None, None, None
 
 
@@ -427,10 +432,13 @@ class GaussianRasterizer(nn.Module):
             raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
         e = means3D.new_empty(0)
         box = options if options is not None else DeferOptions()
-        color, radii = _RasterizeGaussians.apply(
-            means3D, means2D, e if shs is None else shs, e if colors_precomp is None else colors_precomp, opacities,
-            e if scales is None else scales, e if rotations is None else rotations,
-            e if cov3D_precomp is None else cov3D_precomp, self.raster_settings, False, 0.0, False, box)
+        # forward-only by construction: nothing is saved for a backward pass and the frame may be incomplete
+        # until the ticket is validated, so the result must never carry a grad_fn
+        det = lambda t: e if t is None else t.detach()
+        with torch.no_grad():
+            color, radii = _RasterizeGaussians.apply(
+                means3D.detach(), means2D.detach(), det(shs), det(colors_precomp), opacities.detach(), det(scales),
+                det(rotations), det(cov3D_precomp), self.raster_settings, False, 0.0, False, box)
         return color, radii, box[-1]
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None,

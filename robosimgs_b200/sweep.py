@@ -284,8 +284,13 @@ def render_sweep(cameras: Sequence[Camera], render_fn: Callable[[Camera], torch.
         if mine:
             means[torch.tensor(mine)] = torch.stack([dmeans[f] for f in mine]).cpu()
     else:
+        deferred = bool(getattr(render_fn, "deferred", False))
         for f in mine:
             frame = render_fn(cameras[f])
+            if deferred:                     # (frame, ticket): validate at once, re-render exactly on overflow
+                frame, ticket = frame
+                if ticket is not None and not ticket.ok():
+                    frame, _ = render_fn(cameras[f], force_exact=True)
             if on_frame is not None:
                 on_frame(f, frame)
             means[f] = frame.double().mean().item()

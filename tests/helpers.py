@@ -21,6 +21,33 @@ def max_rel_err(got, ref):
     return float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-30))
 
 
+def component_max_rel_err(got, ref):
+    """Second gradient metric, per COMPONENT: for a tensor [P, ...] the per-tensor metric above is evaluated
+    separately for every trailing index (each SH coefficient and colour channel, each axis of a scale, ...),
+    so an error in a small-magnitude component (an SH degree-3 coefficient next to DC) cannot hide behind
+    the tensor's largest element.  Returns the worst component."""
+    ref = np.asarray(ref, np.float64)
+    got = np.asarray(got, np.float64).reshape(ref.shape)
+    P = ref.shape[0]
+    d = np.abs(got - ref).reshape(P, -1).max(axis=0)
+    s = np.abs(ref).reshape(P, -1).max(axis=0)
+    ok = s > 0
+    return float((d[ok] / s[ok]).max()) if ok.any() else 0.0
+
+
+def elementwise_violations(got, ref, rtol=1e-3, atol_frac=1e-4):
+    """Element-wise gradient bound: fraction of elements with |got - ref| > rtol |ref| + atol_frac * (max |ref| of
+    the element's component).  fp32 accumulation over thousands of pixel terms leaves an absolute error that
+    scales with the component, not with the element, hence the small absolute floor."""
+    ref = np.asarray(ref, np.float64)
+    got = np.asarray(got, np.float64).reshape(ref.shape)
+    P = ref.shape[0]
+    r2, g2 = ref.reshape(P, -1), got.reshape(P, -1)
+    floor = atol_frac * np.abs(r2).max(axis=0, keepdims=True)
+    bad = np.abs(g2 - r2) > rtol * np.abs(r2) + floor
+    return float(bad.mean())
+
+
 def small_scene(P=400, seed=5, degree=3, W=72, H=56, big=20, fov=60.0, eye=(0.5, 0.3, 2.5),
                 bg=(0.2, 0.1, 0.4), scale_modifier=1.0, opacity_boost=0.0):
     sc, _ = cube_scene(P=P, seed=seed, degree=degree)

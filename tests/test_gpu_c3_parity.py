@@ -1,0 +1,225 @@
+"""Parity on the BENCHMARKED configuration: BASELINE config C3 -- the 1M-Gaussian room at
+1920x1080, SH degree 3 -- rendered with exactly the option set bench.py times (policy-chosen bins, default pair
+sort, four-pixel compositing kernels, SceneRenderer with CUDA-graph replay and the deferred pair check), against
+the fp32 and fp64 CPU oracle on the same seeded scene; gradients of the train step against the fp64 oracle adjoint.
+
+Tolerances (BASELINE.json north_star): PSNR >= 60 dB; gradient max-rel-err < 1e-3 per tensor, plus the
+per-component and element-wise bounds of tests/helpers.py.  The measured values are written to
+gpurun_out/c3_parity.json so the round's record carries them.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import component_max_rel_err, elementwise_violations, max_rel_err, psnr
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NAMES = ("means3D", "shs", "opacities", "scales", "rotations")
+RECORD = {}
+
+
+@pytest.fixture(scope="module")
+def c3(built):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from oracle import gs_oracle
+    from robosimgs_b200 import _cabi
+    from robosimgs_b200.scenes import room_scene, room_target, settings_from_camera
+    _cabi.lib()
+    for opt in ("render", "bin_shift", "binning"):
+        _cabi.set_option(opt, -1)                     # library defaults, as bench.py runs
+    gs_oracle.set_num_threads(os.cpu_count() or 1)
+    sc, cam = room_scene()
+    rs = settings_from_camera(cam, 3)
+    kw = dict(shs=sc.shs, scales=sc.scales, rotations=sc.rotations)
+    st32 = gs_oracle.forward(rs, sc.means3D, sc.opacities, dtype=np.float32, **kw)
+    st64 = gs_oracle.forward(rs, sc.means3D, sc.opacities, dtype=np.float64, **kw)
+    dev = torch.device("cuda:0")
+    tens = {k: getattr(sc, k).to(dev) for k in NAMES}
+    yield dict(sc=sc, cam=cam, st32=st32, st64=st64, tens=tens, dev=dev, target=room_target(), oracle=gs_oracle)
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "c3_parity.json"), "w") as f:
+            json.dump(RECORD, f, indent=1)
+    except OSError:
+        pass
+
+
+def _policy_shift(dev, P, H, W):
+    from robosimgs_b200 import rasterizer
+    pol = rasterizer._BIN_POLICY.get((dev.index, P, H, W))
+    return None if pol is None else pol["shift"]
+
+
+def test_c3_forward_through_the_bench_path_matches_oracle(c3):
+    """SceneRenderer exactly as bench.py's headline uses it: 4 streams, one captured CUDA graph per frame slot,
+    deferred pair check, cameras resident, frames stay on the device; policy-chosen bins."""
+    from robosimgs_b200.sweep import SceneRenderer
+    dev, cam, tens = c3["dev"], c3["cam"], c3["tens"]
+    H, W = cam.image_height, cam.image_width
+    r = SceneRenderer(tens, 3, torch.zeros(3, device=dev), H, W, streams=4, graphs=True, host_frames=False)
+    block = torch.cat([cam.viewmatrix.reshape(-1), cam.projmatrix.reshape(-1), cam.campos.reshape(-1)]).to(dev)
+    frames = []
+    with torch.no_grad():
+        for _ in range(3):                                  # exact frame, graph capture, graph replay on every slot
+            hs = [r.submit(cam, cam_block=block) for _ in range(r.in_flight_limit())]
+            frames = [r.collect(h).clone() for h in hs]
+    torch.cuda.synchronize()
+    assert all(s["graph"] is not None for s in r.slots), "frames were not graph replays"
+    assert r.redone == 0
+    shift = _policy_shift(dev, tens["means3D"].shape[0], H, W)
+    img = frames[-1].cpu().numpy()
+    for f in frames[:-1]:
+        assert torch.equal(f, frames[-1]), "graph replays of the same camera differ"
+    p32, p64 = psnr(img, c3["st32"].color), psnr(img, c3["st64"].color)
+    RECORD["forward_bench_path"] = dict(psnr_db_vs_f32_oracle=p32, psnr_db_vs_f64_oracle=p64, policy_bin_shift=shift,
+                                        pair_capacity=r.capacity, max_abs_err=float(np.abs(img - c3["st64"].color).max()))
+    assert p32 >= 60.0 and p64 >= 60.0, (p32, p64)
+    assert np.abs(img - c3["st64"].color).max() < 5e-3      # a wrongly ordered or dropped splat shows up far above
+
+
+def test_c3_radii_alpha_and_projection_fields_match_oracle(c3):
+    """Operator call with the converged policy: radii, 1 - final_T, and every field the projection stage writes
+    (pixel centre, conic, opacity, colour, depth bits, clamp mask) against the oracle."""
+    from robosimgs_b200 import _cabi
+    from robosimgs_b200.rasterizer import _RasterizeGaussians
+    from robosimgs_b200.scenes import settings_from_camera
+    dev, cam, tens, st32, st64 = c3["dev"], c3["cam"], c3["tens"], c3["st32"], c3["st64"]
+    rs = settings_from_camera(cam, 3, device=dev)
+    P = tens["means3D"].shape[0]
+    m3 = tens["means3D"].detach().requires_grad_(True)
+    e = m3.new_empty(0)
+    color, radii, alpha = _RasterizeGaussians.apply(m3, torch.zeros_like(m3), tens["shs"], e, tens["opacities"],
+                                                    tens["scales"], tens["rotations"], e, rs, True, 0.0, True)
+    geom = color.grad_fn.saved_tensors[8]
+    torch.cuda.synchronize()
+    radii = radii.cpu().numpy()
+    mism = float((radii != st32.radii).mean())
+    vis_agree = float(((radii > 0) == (st32.radii > 0)).mean())
+    a_err = float(np.abs(alpha.cpu().numpy() - (1.0 - st64.final_T)).max())
+    lay = _cabi.geom_layout(P)
+    gb = geom.cpu().numpy()
+    rec = gb[lay["rec"]:lay["rec"] + P * 48].view(np.float32).reshape(P, 12)
+    depth_bits = gb[lay["depth_key"]:lay["depth_key"] + 4 * P].view(np.uint32)
+    tiles = gb[lay["tiles"]:lay["tiles"] + 4 * P].view(np.uint32)
+    clamped = gb[lay["clamped"]:lay["clamped"] + P]
+    live = (tiles > 0) & (st32.radii > 0)
+    assert live.sum() > 300_000
+    # every Gaussian the oracle gives a radius but the CUDA path gives no bin must be one whose ellipse of
+    # alpha >= 1/255 misses the image; it can never be MORE than the oracle's set
+    assert not ((tiles > 0) & (st32.radii <= 0)).any()
+    xy = np.abs(rec[live, 0:2] - st64.xy[live]).max()
+    con = st64.conic_opacity[live]
+    conic_rel = (np.abs(rec[live][:, [2, 3, 4]] - con[:, :3]) / (np.abs(con[:, :3]) + 1e-6 * np.abs(con[:, :3]).max())).max()
+    opac = np.abs(rec[live, 5] - con[:, 3]).max()
+    rgb = np.abs(rec[live, 8:11] - st64.rgb[live]).max()
+    idx_ok = bool((rec[live, 7].view(np.uint32) == np.nonzero(live)[0].astype(np.uint32)).all())
+    rad_ok = float((rec[live, 11].astype(np.int32) == radii[live]).mean())
+    d32 = st32.depths.astype(np.float32).view(np.uint32)
+    depth_ulps = np.abs(depth_bits[live].astype(np.int64) - d32[live].astype(np.int64)).max()
+    cl_o = (st32.clamped[:, 0] | (st32.clamped[:, 1] << 1) | (st32.clamped[:, 2] << 2)).astype(np.uint8)
+    clamp_mism = float((clamped[live] != cl_o[live]).mean())
+    RECORD["projection_fields"] = dict(radii_mismatch=mism, visible_agreement=vis_agree, alpha_max_abs_err=a_err,
+                                       xy_max_abs_px=float(xy), conic_max_rel=float(conic_rel), opacity_max_abs=float(opac),
+                                       rgb_max_abs=float(rgb), depth_max_ulps=int(depth_ulps), clamp_mask_mismatch=clamp_mism,
+                                       live=int(live.sum()))
+    assert mism <= 1e-3 and vis_agree >= 0.999
+    assert a_err < 2e-3
+    assert xy < 2e-3                      # pixels; fp32 projection of coordinates up to 1920
+    assert conic_rel < 2e-3
+    assert opac == 0.0 and idx_ok and rad_ok == 1.0
+    assert rgb < 1e-5
+    assert depth_ulps <= 4                # FMA contraction differs between nvcc and gcc
+    assert clamp_mism < 1e-4
+
+
+@pytest.mark.parametrize("loss_kind", ["weights", "bench_mse"])
+def test_c3_train_step_gradients_match_fp64_oracle(c3, loss_kind):
+    """fwd + loss + bwd through the public operator on the C3 camera (what bench.py's `train` times) vs
+    gs_oracle.backward in fp64.  'weights': L = sum(color * w), w fixed noise; 'bench_mse': the fused MSE loss of
+    the bench's train step, the oracle adjoint fed with dL/dcolor = 2 (color_gpu - target) / N."""
+    from robosimgs_b200 import GaussianRasterizer
+    from robosimgs_b200.losses import mse_loss as fused_mse_loss
+    from robosimgs_b200.scenes import settings_from_camera
+    dev, cam, tens, st64, gs_oracle = c3["dev"], c3["cam"], c3["tens"], c3["st64"], c3["oracle"]
+    rs = settings_from_camera(cam, 3, device=dev)
+    leaves = {k: tens[k].detach().clone().requires_grad_(True) for k in NAMES}
+    m2 = torch.zeros_like(leaves["means3D"], requires_grad=True)
+    target = c3["target"]
+    for _ in range(2):                                       # second pass runs with the pair hint (no host stall)
+        for t in list(leaves.values()) + [m2]:
+            t.grad = None
+        color, _ = GaussianRasterizer(rs)(leaves["means3D"], m2, leaves["opacities"], shs=leaves["shs"],
+                                          scales=leaves["scales"], rotations=leaves["rotations"])
+        if loss_kind == "weights":
+            (color * target.to(dev)).sum().backward()
+            dL = target.numpy()
+        else:
+            fused_mse_loss(color, target.to(dev)).backward()
+            dL = (2.0 * (color.detach().cpu().double() - target.double()) / target.numel()).numpy()
+    torch.cuda.synchronize()
+    ref = gs_oracle.backward(st64, dL)
+    rec = {}
+    leaves["means2D"] = m2
+    for n in NAMES + ("means2D",):
+        r = getattr(ref, n)
+        g = leaves[n].grad.detach().cpu().numpy().reshape(r.shape)
+        rec[n] = dict(max_rel_err=max_rel_err(g, r), component_max_rel_err=component_max_rel_err(g, r),
+                      elementwise_violation_fraction=elementwise_violations(g, r))
+    RECORD["train_gradients_" + loss_kind] = rec
+    for n, m in rec.items():
+        assert m["max_rel_err"] < 1e-3, (n, m)
+        assert m["component_max_rel_err"] < 2e-3, (n, m)
+        assert m["elementwise_violation_fraction"] < 1e-3, (n, m)
+
+
+def test_c4_sweep_frames_match_oracle(built):
+    """BASELINE config C4 (3M-Gaussian scene, 1080p orbit): two cameras of the 64-camera sweep, rendered through
+    SceneRenderer with HOST frames (the path `python -m robosimgs_b200.sweep` times), against the fp32 oracle after the
+    same 8-bit quantisation; the orbit changes the pair count from frame to frame, so the capacity protocol is live."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from oracle import gs_oracle
+    from robosimgs_b200.scenes import settings_from_camera, sweep_scene
+    from robosimgs_b200.sweep import SceneRenderer
+    gs_oracle.set_num_threads(os.cpu_count() or 1)
+    dev = torch.device("cuda:0")
+    sc, cams = sweep_scene(3_000_000, 64)
+    tens = {k: getattr(sc, k).to(dev) for k in NAMES}
+    H, W = cams[0].image_height, cams[0].image_width
+    r = SceneRenderer(tens, 3, torch.zeros(3, device=dev), H, W, streams=4, graphs=True)
+    pick = (5, 37)
+    got = {}
+    order = [f for f in range(0, 64, 8) if f not in pick] + list(pick)
+    with torch.no_grad():
+        for rep in range(2):
+            pend = []
+            for f in order + [None] * r.in_flight_limit():
+                while pend and (f is None or len(pend) >= r.in_flight_limit()):
+                    g, h = pend.pop(0)
+                    frame = r.collect(h)
+                    if g in pick:
+                        got[g] = frame.clone().numpy()
+                if f is not None:
+                    pend.append((f, r.submit(cams[f])))
+    rec = {}
+    for f in pick:
+        st = gs_oracle.forward(settings_from_camera(cams[f], 3), sc.means3D, sc.opacities, shs=sc.shs, scales=sc.scales,
+                               rotations=sc.rotations, dtype=np.float32)
+        ref8 = np.clip(np.rint(np.clip(st.color, 0, 1) * 255.0), 0, 255).astype(np.uint8).transpose(1, 2, 0)
+        diff = np.abs(got[f].astype(np.int16) - ref8.astype(np.int16))
+        rec[f] = dict(psnr_db_8bit=psnr(got[f] / 255.0, ref8 / 255.0), max_levels=int(diff.max()),
+                      frac_pixels_off_by_one=float((diff > 0).mean()), pairs_reference=int(st.num_rendered))
+        assert diff.max() <= 1 and (diff > 0).mean() < 1e-3, rec[f]
+    RECORD["c4_host_frames"] = dict(frames=rec, frames_rendered_twice=r.redone)
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "c4_parity.json"), "w") as fjs:
+            json.dump(RECORD["c4_host_frames"], fjs, indent=1)
+    except OSError:
+        pass
