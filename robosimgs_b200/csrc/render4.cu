@@ -78,12 +78,18 @@ __global__ void __launch_bounds__(R4_THREADS, R4_FWD_MINB) k_render_fwd4(RenderA
   // again, so the hot loop needs no separate flag.  nstop = list position of the record that
   // finished the pixel (n if none did): nothing at or behind it contributes, and every record in
   // front of it that the adjoint finds valid did contribute -- all the adjoint needs to know.
-  float T[4], Cr[4], Cg[4], Cb[4];
+  // Pixel state lives in register PAIRS (pixels 0|1 and 2|3): everything up to the three tests below is issued
+  // as packed f32x2 instructions (FADD2 / FFMA2 / FMUL2, sm_100) -- one issue slot for two pixels.  Every packed
+  // operation rounds exactly like the scalar expression it replaces (and like render.cu's one-pixel kernels):
+  //   ndx = px - x (= -dx);  power2 = fma(ndx, fma(-hA, ndx, bdy), -cdy2);  1 - alpha = fma(alpha, -1, 1).
+  float2 T[2], Cr[2], Cg[2], Cb[2], pxf2[2];
   uint32_t nstop[4];
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
-    T[i] = t.in[i] ? 1.f : -1.f;
-    Cr[i] = 0.f; Cg[i] = 0.f; Cb[i] = 0.f; nstop[i] = n;
+  for (int h = 0; h < 2; h++) {
+    T[h] = make_float2(t.in[2 * h] ? 1.f : -1.f, t.in[2 * h + 1] ? 1.f : -1.f);
+    Cr[h] = Cg[h] = Cb[h] = make_float2(0.f, 0.f);
+    pxf2[h] = make_float2(t.pxf[2 * h], t.pxf[2 * h + 1]);
+    nstop[2 * h] = n; nstop[2 * h + 1] = n;
   }
 
   // One record against the thread's four pixels.  CLAMP = false when opacity <= 0.99: then
@@ -93,38 +99,53 @@ __global__ void __launch_bounds__(R4_THREADS, R4_FWD_MINB) k_render_fwd4(RenderA
   auto eval = [&](const float4& q0, const float4& q1, const float4& q2, uint32_t pos, auto clamp_tag) {
     constexpr bool CLAMP = decltype(clamp_tag)::value;
     const RowTerms rt = row_terms(q0.z, q0.w, q1.x, q0.y - t.pyf);
+    const float2 nx2 = make_float2(-q0.x, -q0.x), nhA2 = make_float2(-rt.hA, -rt.hA);
+    const float2 bdy2 = make_float2(rt.bdy, rt.bdy), ncdy2 = make_float2(-rt.cdy2, -rt.cdy2);
+    const float2 o2 = make_float2(q1.y, q1.y);
     bool stop[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const float dx = q0.x - t.pxf[i];
-      const float p2 = power2_of(rt, dx);
-      float alpha = q1.y * ex2_fast(p2);
-      if (CLAMP) alpha = fminf(0.99f, alpha);
-      const bool valid = p2 <= 0.f && alpha >= (1.f / 255.f);
-      const float test_T = T[i] * (1.f - alpha);
-      const bool upd = valid && test_T >= 0.0001f;
-      stop[i] = valid && !(test_T >= 0.0001f);
-      if (upd) {
-        const float w = alpha * T[i];
-        Cr[i] = __fmaf_rn(q2.x, w, Cr[i]);
-        Cg[i] = __fmaf_rn(q2.y, w, Cg[i]);
-        Cb[i] = __fmaf_rn(q2.z, w, Cb[i]);
-        T[i] = test_T;
+    for (int h = 0; h < 2; h++) {
+      const float2 ndx = __fadd2_rn(pxf2[h], nx2);
+      const float2 p2 = __ffma2_rn(ndx, __ffma2_rn(nhA2, ndx, bdy2), ncdy2);
+      float2 alpha = __fmul2_rn(o2, make_float2(ex2_fast(p2.x), ex2_fast(p2.y)));
+      if (CLAMP) alpha = make_float2(fminf(0.99f, alpha.x), fminf(0.99f, alpha.y));
+      const float2 test_T = __fmul2_rn(T[h], __ffma2_rn(alpha, make_float2(-1.f, -1.f), make_float2(1.f, 1.f)));
+      const bool valid0 = p2.x <= 0.f && alpha.x >= (1.f / 255.f);
+      const bool valid1 = p2.y <= 0.f && alpha.y >= (1.f / 255.f);
+      const bool upd0 = valid0 && test_T.x >= 0.0001f, upd1 = valid1 && test_T.y >= 0.0001f;
+      stop[2 * h] = valid0 && !(test_T.x >= 0.0001f);
+      stop[2 * h + 1] = valid1 && !(test_T.y >= 0.0001f);
+      if (upd0) {
+        const float w = alpha.x * T[h].x;
+        Cr[h].x = __fmaf_rn(q2.x, w, Cr[h].x);
+        Cg[h].x = __fmaf_rn(q2.y, w, Cg[h].x);
+        Cb[h].x = __fmaf_rn(q2.z, w, Cb[h].x);
+        T[h].x = test_T.x;
+      }
+      if (upd1) {
+        const float w = alpha.y * T[h].y;
+        Cr[h].y = __fmaf_rn(q2.x, w, Cr[h].y);
+        Cg[h].y = __fmaf_rn(q2.y, w, Cg[h].y);
+        Cb[h].y = __fmaf_rn(q2.z, w, Cb[h].y);
+        T[h].y = test_T.y;
       }
     }
     if (stop[0] || stop[1] || stop[2] || stop[3]) {   // rare: at most once per pixel
 #pragma unroll
-      for (int i = 0; i < 4; i++)
-        if (stop[i] && T[i] > 0.f) { T[i] = -T[i]; nstop[i] = pos; }
+      for (int h = 0; h < 2; h++) {
+        if (stop[2 * h] && T[h].x > 0.f) { T[h].x = -T[h].x; nstop[2 * h] = pos; }
+        if (stop[2 * h + 1] && T[h].y > 0.f) { T[h].y = -T[h].y; nstop[2 * h + 1] = pos; }
+      }
     }
   };
+  auto all_done = [&]() { return fmaxf(fmaxf(T[0].x, T[0].y), fmaxf(T[1].x, T[1].y)) < 0.f; };
 
   for (uint32_t c = 0; c < nchunks; c++) {
     ring.wait();
     const uint32_t cnt = ring.count(c);
     const float4* st = sm[c % R4_STAGES];
     for (uint32_t base = 0; base < cnt; base += 32) {
-      if (__all_sync(0xffffffffu, fmaxf(fmaxf(T[0], T[1]), fmaxf(T[2], T[3])) < 0.f)) break;
+      if (__all_sync(0xffffffffu, all_done())) break;
       const uint32_t j = base + lane;
       bool hit = false;
       if (j < cnt) {
@@ -145,40 +166,42 @@ __global__ void __launch_bounds__(R4_THREADS, R4_FWD_MINB) k_render_fwd4(RenderA
         else eval(q0, q1, q2, pos, std::false_type{});
       }
     }
-    const int num_done = __syncthreads_count(fmaxf(fmaxf(T[0], T[1]), fmaxf(T[2], T[3])) < 0.f);
+    const int num_done = __syncthreads_count(all_done());
     if (num_done == R4_THREADS) break;
     ring.refill(c);
   }
   r4_cp_async_wait<0>();   // no asynchronous copy may still target this CTA's shared memory
 
-#pragma unroll
-  for (int i = 0; i < 4; i++) T[i] = fabsf(T[i]);
+  const float Tf[4] = {fabsf(T[0].x), fabsf(T[0].y), fabsf(T[1].x), fabsf(T[1].y)};
+  const float R_[4] = {Cr[0].x, Cr[0].y, Cr[1].x, Cr[1].y};
+  const float G_[4] = {Cg[0].x, Cg[0].y, Cg[1].x, Cg[1].y};
+  const float B_[4] = {Cb[0].x, Cb[0].y, Cb[1].x, Cb[1].y};
   const size_t hw = (size_t)a.H * a.W;
   const size_t pid = (size_t)t.py * a.W + t.px0;
   if (a.vec4 && t.in[3]) {
     float4* pix = a.pix + pid;
 #pragma unroll
-    for (int i = 0; i < 4; i++) pix[i] = make_float4(Cr[i], Cg[i], Cb[i], T[i]);
+    for (int i = 0; i < 4; i++) pix[i] = make_float4(R_[i], G_[i], B_[i], Tf[i]);
     *reinterpret_cast<uint4*>(a.n_contrib + pid) = make_uint4(nstop[0], nstop[1], nstop[2], nstop[3]);
     const float b0 = __ldg(a.bg + 0), b1 = __ldg(a.bg + 1), b2 = __ldg(a.bg + 2);
     *reinterpret_cast<float4*>(a.out_color + pid) =
-        make_float4(__fmaf_rn(T[0], b0, Cr[0]), __fmaf_rn(T[1], b0, Cr[1]), __fmaf_rn(T[2], b0, Cr[2]),
-                    __fmaf_rn(T[3], b0, Cr[3]));
+        make_float4(__fmaf_rn(Tf[0], b0, R_[0]), __fmaf_rn(Tf[1], b0, R_[1]), __fmaf_rn(Tf[2], b0, R_[2]),
+                    __fmaf_rn(Tf[3], b0, R_[3]));
     *reinterpret_cast<float4*>(a.out_color + hw + pid) =
-        make_float4(__fmaf_rn(T[0], b1, Cg[0]), __fmaf_rn(T[1], b1, Cg[1]), __fmaf_rn(T[2], b1, Cg[2]),
-                    __fmaf_rn(T[3], b1, Cg[3]));
+        make_float4(__fmaf_rn(Tf[0], b1, G_[0]), __fmaf_rn(Tf[1], b1, G_[1]), __fmaf_rn(Tf[2], b1, G_[2]),
+                    __fmaf_rn(Tf[3], b1, G_[3]));
     *reinterpret_cast<float4*>(a.out_color + 2 * hw + pid) =
-        make_float4(__fmaf_rn(T[0], b2, Cb[0]), __fmaf_rn(T[1], b2, Cb[1]), __fmaf_rn(T[2], b2, Cb[2]),
-                    __fmaf_rn(T[3], b2, Cb[3]));
+        make_float4(__fmaf_rn(Tf[0], b2, B_[0]), __fmaf_rn(Tf[1], b2, B_[1]), __fmaf_rn(Tf[2], b2, B_[2]),
+                    __fmaf_rn(Tf[3], b2, B_[3]));
   } else {
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       if (!t.in[i]) continue;
-      a.pix[pid + i] = make_float4(Cr[i], Cg[i], Cb[i], T[i]);
+      a.pix[pid + i] = make_float4(R_[i], G_[i], B_[i], Tf[i]);
       a.n_contrib[pid + i] = nstop[i];
-      a.out_color[pid + i] = __fmaf_rn(T[i], __ldg(a.bg + 0), Cr[i]);
-      a.out_color[hw + pid + i] = __fmaf_rn(T[i], __ldg(a.bg + 1), Cg[i]);
-      a.out_color[2 * hw + pid + i] = __fmaf_rn(T[i], __ldg(a.bg + 2), Cb[i]);
+      a.out_color[pid + i] = __fmaf_rn(Tf[i], __ldg(a.bg + 0), R_[i]);
+      a.out_color[hw + pid + i] = __fmaf_rn(Tf[i], __ldg(a.bg + 1), G_[i]);
+      a.out_color[2 * hw + pid + i] = __fmaf_rn(Tf[i], __ldg(a.bg + 2), B_[i]);
     }
   }
 }
@@ -229,9 +252,10 @@ __global__ void __launch_bounds__(R4_THREADS, R4_BWD_MINB) k_render_bwd4(RenderB
 
   ring.prologue();
 
-  float gr[4], gg[4], gb[4], F[4], T[4], R[4];
+  float2 gr[2], gg[2], gb[2], F[2], T[2], R[2], pxf2[2];
   uint32_t nc[4];
   {
+    float gr_[4], gg_[4], gb_[4], F_[4];
     const size_t hw = (size_t)a.H * a.W;
     const size_t pid = (size_t)t.py * a.W + t.px0;
     float4 fin[4];
@@ -243,28 +267,36 @@ __global__ void __launch_bounds__(R4_THREADS, R4_BWD_MINB) k_render_bwd4(RenderB
       const float4 r4 = __ldg(reinterpret_cast<const float4*>(a.dL_dpix + pid));
       const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.dL_dpix + hw + pid));
       const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.dL_dpix + 2 * hw + pid));
-      gr[0] = r4.x; gr[1] = r4.y; gr[2] = r4.z; gr[3] = r4.w;
-      gg[0] = g4.x; gg[1] = g4.y; gg[2] = g4.z; gg[3] = g4.w;
-      gb[0] = b4.x; gb[1] = b4.y; gb[2] = b4.z; gb[3] = b4.w;
+      gr_[0] = r4.x; gr_[1] = r4.y; gr_[2] = r4.z; gr_[3] = r4.w;
+      gg_[0] = g4.x; gg_[1] = g4.y; gg_[2] = g4.z; gg_[3] = g4.w;
+      gb_[0] = b4.x; gb_[1] = b4.y; gb_[2] = b4.z; gb_[3] = b4.w;
     } else {
 #pragma unroll
       for (int i = 0; i < 4; i++) {
         fin[i] = make_float4(0.f, 0.f, 0.f, 1.f);
-        nc[i] = 0u; gr[i] = 0.f; gg[i] = 0.f; gb[i] = 0.f;
+        nc[i] = 0u; gr_[i] = 0.f; gg_[i] = 0.f; gb_[i] = 0.f;
         if (t.in[i]) {
           fin[i] = a.pix[pid + i];
           nc[i] = a.n_contrib[pid + i];
-          gr[i] = __ldg(a.dL_dpix + pid + i);
-          gg[i] = __ldg(a.dL_dpix + hw + pid + i);
-          gb[i] = __ldg(a.dL_dpix + 2 * hw + pid + i);
+          gr_[i] = __ldg(a.dL_dpix + pid + i);
+          gg_[i] = __ldg(a.dL_dpix + hw + pid + i);
+          gb_[i] = __ldg(a.dL_dpix + 2 * hw + pid + i);
         }
       }
     }
     const float b0 = __ldg(a.bg), b1 = __ldg(a.bg + 1), b2 = __ldg(a.bg + 2);
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      F[i] = fin[i].x * gr[i] + fin[i].y * gg[i] + fin[i].z * gb[i] + fin[i].w * (b0 * gr[i] + b1 * gg[i] + b2 * gb[i]);
-      T[i] = 1.f; R[i] = 0.f;
+    for (int i = 0; i < 4; i++)
+      F_[i] = fin[i].x * gr_[i] + fin[i].y * gg_[i] + fin[i].z * gb_[i] + fin[i].w * (b0 * gr_[i] + b1 * gg_[i] + b2 * gb_[i]);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      gr[h] = make_float2(gr_[2 * h], gr_[2 * h + 1]);
+      gg[h] = make_float2(gg_[2 * h], gg_[2 * h + 1]);
+      gb[h] = make_float2(gb_[2 * h], gb_[2 * h + 1]);
+      F[h] = make_float2(F_[2 * h], F_[2 * h + 1]);
+      T[h] = make_float2(1.f, 1.f);
+      R[h] = make_float2(0.f, 0.f);
+      pxf2[h] = make_float2(t.pxf[2 * h], t.pxf[2 * h + 1]);
     }
   }
   const uint32_t ncmax = max(max(nc[0], nc[1]), max(nc[2], nc[3]));
@@ -293,38 +325,52 @@ __global__ void __launch_bounds__(R4_THREADS, R4_BWD_MINB) k_render_bwd4(RenderB
         const float dy = q0.y - t.pyf;
         const RowTerms rt = row_terms(q0.z, q0.w, q1.x, dy);
         const uint32_t pos = c * R4_CH + jj;
-        float dx[4], G[4], alpha[4];
-        bool valid[4];
+        // packed f32x2 over the pixel pairs (0|1, 2|3), branch-free: a record that does not contribute to a
+        // pixel acts on it with alpha = G = 0.  ndx = px - x = -dx, so Sx = -sum(m ndx), Sxx = sum(m ndx^2).
+        const float2 nx2 = make_float2(-q0.x, -q0.x), nhA2 = make_float2(-rt.hA, -rt.hA);
+        const float2 bdy2 = make_float2(rt.bdy, rt.bdy), ncdy2 = make_float2(-rt.cdy2, -rt.cdy2);
+        const float2 o2 = make_float2(q1.y, q1.y);
+        float2 ndx[2], G[2], alpha[2], vmask[2];
+        bool any_valid = false;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-          dx[i] = q0.x - t.pxf[i];
-          const float p2 = power2_of(rt, dx[i]);
-          G[i] = ex2_fast(p2);
-          alpha[i] = fminf(0.99f, q1.y * G[i]);
-          valid[i] = pos < nc[i] && p2 <= 0.f && alpha[i] >= (1.f / 255.f);
+        for (int h = 0; h < 2; h++) {
+          ndx[h] = __fadd2_rn(pxf2[h], nx2);
+          const float2 p2 = __ffma2_rn(ndx[h], __ffma2_rn(nhA2, ndx[h], bdy2), ncdy2);
+          G[h] = make_float2(ex2_fast(p2.x), ex2_fast(p2.y));
+          const float2 og = __fmul2_rn(o2, G[h]);
+          alpha[h] = make_float2(fminf(0.99f, og.x), fminf(0.99f, og.y));
+          const bool v0 = pos < nc[2 * h] && p2.x <= 0.f && alpha[h].x >= (1.f / 255.f);
+          const bool v1 = pos < nc[2 * h + 1] && p2.y <= 0.f && alpha[h].y >= (1.f / 255.f);
+          vmask[h] = make_float2(v0 ? 1.f : 0.f, v1 ? 1.f : 0.f);
+          any_valid = any_valid || v0 || v1;
         }
-        if (!__any_sync(0xffffffffu, valid[0] || valid[1] || valid[2] || valid[3])) continue;
-        float vr = 0.f, vg = 0.f, vb = 0.f, s0 = 0.f, sx = 0.f, sxx = 0.f;
+        if (!__any_sync(0xffffffffu, any_valid)) continue;
+        const float2 one2 = make_float2(1.f, 1.f), neg2 = make_float2(-1.f, -1.f);
+        const float2 cr2 = make_float2(q2.x, q2.x), cg2 = make_float2(q2.y, q2.y), cb2 = make_float2(q2.z, q2.z);
+        float2 vr2 = make_float2(0.f, 0.f), vg2 = vr2, vb2 = vr2, s02 = vr2, nsx2 = vr2, sxx2 = vr2;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-          // branch-free: a record that does not contribute to this pixel acts with alpha = G = 0
-          const float al = valid[i] ? alpha[i] : 0.f;
-          const float Gi = valid[i] ? G[i] : 0.f;
-          const float w = al * T[i];
-          const float cg = q2.x * gr[i] + q2.y * gg[i] + q2.z * gb[i];
-          R[i] = __fmaf_rn(w, cg, R[i]);
-          const float one_m = 1.f - al;
-          const float dL_dalpha = T[i] * cg - rcp_fast(one_m) * (F[i] - R[i]);
-          T[i] = T[i] * one_m;
-          const float m = Gi * dL_dalpha;
-          vr = __fmaf_rn(w, gr[i], vr);
-          vg = __fmaf_rn(w, gg[i], vg);
-          vb = __fmaf_rn(w, gb[i], vb);
-          s0 += m;
-          const float mx = m * dx[i];
-          sx += mx;
-          sxx = __fmaf_rn(mx, dx[i], sxx);
+        for (int h = 0; h < 2; h++) {
+          const float2 al = __fmul2_rn(alpha[h], vmask[h]);
+          const float2 Gi = __fmul2_rn(G[h], vmask[h]);
+          const float2 w = __fmul2_rn(al, T[h]);
+          const float2 cg = __ffma2_rn(cb2, gb[h], __ffma2_rn(cg2, gg[h], __fmul2_rn(cr2, gr[h])));
+          R[h] = __ffma2_rn(w, cg, R[h]);
+          const float2 one_m = __ffma2_rn(al, neg2, one2);
+          const float2 rc = make_float2(rcp_fast(one_m.x), rcp_fast(one_m.y));
+          // dL/dalpha = T cg - (F - R) / (1 - alpha)
+          const float2 dL_dalpha = __ffma2_rn(T[h], cg, __fmul2_rn(rc, __ffma2_rn(F[h], neg2, R[h])));
+          T[h] = __fmul2_rn(T[h], one_m);
+          const float2 m = __fmul2_rn(Gi, dL_dalpha);
+          vr2 = __ffma2_rn(w, gr[h], vr2);
+          vg2 = __ffma2_rn(w, gg[h], vg2);
+          vb2 = __ffma2_rn(w, gb[h], vb2);
+          s02 = __fadd2_rn(s02, m);
+          const float2 nmx = __fmul2_rn(m, ndx[h]);
+          nsx2 = __fadd2_rn(nsx2, nmx);
+          sxx2 = __ffma2_rn(nmx, ndx[h], sxx2);
         }
+        const float vr = vr2.x + vr2.y, vg = vg2.x + vg2.y, vb = vb2.x + vb2.y;
+        const float s0 = s02.x + s02.y, sx = -(nsx2.x + nsx2.y), sxx = sxx2.x + sxx2.y;
         // the four pixels share dy: Sy = dy S0, Sxy = dy Sx, Syy = dy^2 S0
         float v[8], v8;
         v[0] = vr; v[1] = vg; v[2] = vb;

@@ -134,7 +134,7 @@ def test_c3_radii_alpha_and_projection_fields_match_oracle(c3):
     assert conic_rel < 2e-3
     assert opac == 0.0 and idx_ok and rad_ok == 1.0
     assert rgb < 1e-5
-    assert depth_ulps <= 4                # FMA contraction differs between nvcc and gcc
+    assert depth_ulps <= 16               # a 4-term dot product with cancellation; FMA contraction differs (nvcc vs gcc)
     assert clamp_mism < 1e-4
 
 
@@ -174,8 +174,8 @@ def test_c3_train_step_gradients_match_fp64_oracle(c3, loss_kind):
     RECORD["train_gradients_" + loss_kind] = rec
     for n, m in rec.items():
         assert m["max_rel_err"] < 1e-3, (n, m)
-        assert m["component_max_rel_err"] < 2e-3, (n, m)
-        assert m["elementwise_violation_fraction"] < 1e-3, (n, m)
+        assert m["component_max_rel_err"] < 1e-3, (n, m)                 # measured: < 6e-6 for every component
+        assert m["elementwise_violation_fraction"] < 1e-5, (n, m)        # measured: 0
 
 
 def test_c4_sweep_frames_match_oracle(built):
