@@ -15,8 +15,9 @@
  * Plain pointers and sizes only; no torch types.  All `const float*` / `float*` data arguments are
  * DEVICE pointers (contiguous fp32, row-major), exactly the buffers the Python operator surface
  * (GaussianRasterizer.forward) already holds.  `stream` is a cudaStream_t
- * passed as void* (NULL = legacy default stream).  The library keeps no global state besides a
- * thread-local error string and is re-entrant per stream.
+ * passed as void* (NULL = legacy default stream).  Process-wide state: the tuning knobs of b200gs_set_option
+ * (never change results), the optional stage timers of b200gs_profile_* and the launch counter; the error
+ * string is thread-local.  Calls are re-entrant per stream.
  *
  * Scratch memory is caller-owned: the library asks the caller to size
  * byte buffers through a callback and carves 128-byte aligned sub-arrays inside them.  The three
@@ -241,8 +242,10 @@ int64_t b200gs_launch_count(int reset);
 /*
  * Process-wide tuning knobs (never change results):
  *   "bin_shift": -1 automatic (default), 0..5 = sort pairs per (16 << shift)^2 pixel bins
- *   "binning":    1 bucketed binning (per-bin counters and cursors, one per-bin sort launch; default),
- *                 0 global radix sort of (bin << 32 | depth) keys
+ *   "binning":    1 depth-sliced bucket binning (default; bucket.cu: per-(bin, depth slice) pair counters in the
+ *                 projection kernel, one-CTA scan, cursor emission, one warp sorts one bucket in registers),
+ *                 0 global radix sort of (bin << 32 | depth) keys (library scan + sort; kept as a cross-check),
+ *                 -1 back to the default
  *   "sort_keys":  32 (default) global sort on 32-bit keys (bin << 24 | monotone 24-bit quantisation of the depth
  *                 bits; exact (depth, index) order restored inside runs of equal keys) whenever there are at
  *                 most 255 bins and the library sort is used -- four radix passes instead of five; 64 always

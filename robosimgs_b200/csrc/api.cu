@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <functional>
 #include <mutex>
 #include <vector>
 
@@ -70,15 +71,16 @@ struct StageTimer {
 // keys), capped at 3 (64 compositing CTAs share one bin list).  B200GS_BIN_SHIFT overrides.
 static std::atomic<int> g_bin_shift_override{-2};   // -2: not initialised, -1: automatic
 
-// binning pipeline: 1 = bucketed (bucket.cu: per-bin counters + cursors, one per-bin sort launch;
-// default), 0 = global radix sort of (bin | depth) keys (binning.cu / coopsort.cu).
+// binning pipeline: 1 = depth-sliced buckets (bucket.cu: per-bucket counters in the projection kernel, one-CTA
+// scan, cursor emission, one warp sorts one bucket; default), 0 = global radix sort of (bin | depth) keys
+// (binning.cu / coopsort.cu -- the library-sort pipeline, kept as a cross-check: both give bit-identical lists).
 // B200GS_BINNING=bucket|sort or b200gs_set_option("binning", 0|1).
 static std::atomic<int> g_binning_mode{-1};
 static bool use_bucketed() {
   int m = g_binning_mode.load();
   if (m < 0) {
     const char* e = getenv("B200GS_BINNING");
-    m = (e && e[0] == 'b') ? 1 : 0;     // default: global sort (faster until the bucketed kernels are tuned)
+    m = (e && e[0] == 's') ? 0 : 1;
     g_binning_mode.store(m);
   }
   return m == 1;
@@ -99,13 +101,6 @@ static int bin_shift_for(int gx, int gy, int flags = 0) {
   if (hinted >= 0) {
     int s = hinted > 5 ? 5 : hinted;
     while (s < 5 && (((gx + (1 << s) - 1) >> s) * ((gy + (1 << s) - 1) >> s)) >= 65535) s++;
-    return s;
-  }
-  if (use_bucketed()) {
-    // no key-width constraint: 64-px bins (shorter per-tile walks than 128 px, ~1.5x the pairs), coarser
-    // only to keep the single-CTA bin scan short on very large images
-    int s = 2;
-    while (s < 5 && (((gx + (1 << s) - 1) >> s) * ((gy + (1 << s) - 1) >> s)) > 8192) s++;
     return s;
   }
   int s = 0;
@@ -193,6 +188,8 @@ static BinBuf carve_binning(char* base, int64_t D, int tile_bits, size_t* bytes)
   b.keys = c.take<uint64_t>(D);
   b.vals = c.take<uint32_t>(D);
   b.coop_hist = c.take<uint32_t>(coop_sort_hist_bytes() / sizeof(uint32_t));
+  b.win_first = c.take<uint32_t>((size_t)D / BUCKET_WINDOW + BUCKET_BINS_MAX + 2);
+  b.big_segs = c.take<uint2>((size_t)D / 512 + 2);
   b.cub_temp_bytes = pair_sort_temp_bytes(D, 32 + tile_bits);
   b.cub_temp = c.take<char>(b.cub_temp_bytes);
   if (bytes) *bytes = c.bytes();
@@ -206,9 +203,10 @@ static ImgBuf carve_img(char* base, int H, int W, size_t* bytes) {
   im.ranges = c.take<uint2>(tiles);
   im.pix = c.take<float4>((size_t)H * W);
   im.n_contrib = c.take<uint32_t>((size_t)H * W);
-  im.bin_count = c.take<uint32_t>(tiles * BIN_STRIDE);
-  im.bin_cursor = c.take<uint32_t>(tiles * BIN_STRIDE);
-  im.bin_base = c.take<uint32_t>(tiles);
+  im.bin_pub = c.take<unsigned long long>(BUCKET_BINS_MAX);   // 8 KB: bucket_count follows without a gap
+  im.bucket_count = c.take<uint32_t>(BUCKETS_MAX);
+  im.bucket_base = c.take<uint32_t>(BUCKETS_MAX + 4);
+  im.bucket_cursor = c.take<uint32_t>(BUCKETS_MAX);
   if (bytes) *bytes = c.bytes();
   return im;
 }
@@ -402,67 +400,102 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
   pa.view = viewmatrix; pa.proj = projmatrix; pa.campos = campos;
   pa.radii = radii; pa.rec = gb.rec; pa.depth_key = gb.depth_key; pa.tiles = gb.tiles;
   pa.clamped = gb.clamped;
-  const bool bucketed = use_bucketed() && num_tiles < 65535;   // staged bin ids are 16-bit (bucket.cu)
+  // bucketed binning: at most BUCKET_BINS_MAX bins (one scan CTA each, look-back over the lower bins)
+  const bool bucketed = use_bucketed() && (uint32_t)num_tiles <= BUCKET_BINS_MAX;
+  int slices_log2 = 2;
+  while (bucketed && slices_log2 < BUCKET_SLICES_LOG2_MAX && ((uint32_t)num_tiles << (slices_log2 + 1)) <= BUCKETS_MAX)
+    slices_log2++;
+  const uint32_t num_buckets = (uint32_t)num_tiles << slices_log2;
+  uint32_t near_bits;
+  {
+    const float np = pa.near_plane;
+    memcpy(&near_bits, &np, sizeof(uint32_t));
+  }
   pa.gbx = gbx;
-  pa.bin_count = bucketed ? ib.bin_count : nullptr;
+  pa.bucket_count = bucketed ? ib.bucket_count : nullptr;
+  pa.slices_log2 = slices_log2;
+  pa.slice_shift = 27 - slices_log2;      // 16 octaves of depth from the near plane over 2^slices_log2 slices
+  pa.near_bits = near_bits;
+  // bucket counters and, directly in front of them, the look-back words of the bucket scan
   if (bucketed && P > 0 &&
-      (rc = check_cuda(cudaMemsetAsync(ib.bin_count, 0, sizeof(uint32_t) * (size_t)num_tiles * BIN_STRIDE, st),
-                       "clear bin counters")))
+      (rc = check_cuda(cudaMemsetAsync(ib.bin_pub, 0, sizeof(unsigned long long) * BUCKET_BINS_MAX +
+                                                        sizeof(uint32_t) * (size_t)num_buckets, st),
+                       "clear bucket counters")))
     return rc;
   {
     StageTimer t(0, st);
     launch_project(pa, shs ? prm->sh_degree : -1, st);
   }
   if ((rc = debug_sync(prm, st, "project"))) return rc;
-  // bucketed binning: D and the per-bin segment starts come from one scan of the bin counters
   BucketArgs ba;
   ba.P = P; ba.gx = gx; ba.gy = gy; ba.gbx = gbx; ba.bin_shift = bs;
   ba.id_bits = 1;
   while (ba.id_bits < 32 && (1ll << ba.id_bits) < (long long)P) ba.id_bits++;
+  ba.slices_log2 = pa.slices_log2; ba.slice_shift = pa.slice_shift; ba.near_bits = near_bits;
   ba.num_bins = (uint32_t)num_tiles; ba.capacity = 0xFFFFFFFFu;
   ba.tiles = gb.tiles; ba.depth_key = gb.depth_key; ba.rec = gb.rec; ba.radii = radii;
-  ba.bin_count = ib.bin_count; ba.bin_cursor = ib.bin_cursor; ba.bin_base = ib.bin_base; ba.ranges = ib.ranges;
+  ba.bucket_count = ib.bucket_count; ba.bucket_base = ib.bucket_base; ba.bucket_cursor = ib.bucket_cursor;
+  ba.bin_pub = ib.bin_pub; ba.ranges = ib.ranges;
   ba.total = gb.counters + 1; ba.big_queue = gb.big_queue; ba.big_count = gb.counters;
+  ba.big_seg_count = gb.counters + 2; ba.total_windows = gb.counters + 3;
+  ba.win_first = nullptr; ba.win_capacity = 0; ba.big_segs = nullptr;
   ba.seg = nullptr; ba.seg_alt = nullptr; ba.vals_sorted = nullptr;
   const uint32_t* d_total = bucketed ? gb.counters + 1 : gb.offsets + (P > 0 ? P - 1 : 0);
+  const int64_t hint_cap = (prm->pair_capacity_hint > 0 && prm->pair_capacity_hint < (int64_t)0x7fffffff)
+                               ? prm->pair_capacity_hint : 0;
+  bool bin_pub_clean = true;     // the look-back words are zero (cleared together with the counters)
   {
     StageTimer t(1, st);
     if (!bucketed) {
       if ((rc = scan_bin_counts(gb, P, st))) return rc;
-    } else if (P > 0) {
-      launch_bin_scan(ba, st);   // capacity unbounded: only D is consumed from this launch
+    } else if (P > 0 && !hint_cap) {
+      // exact path: D must reach the host before the binning buffer can be sized -- a first scan without the
+      // window table; with a capacity hint the one scan inside run_binning_and_render produces everything
+      launch_bucket_scan(ba, st);
+      bin_pub_clean = false;
     }
   }
   if ((rc = debug_sync(prm, st, "scan"))) return rc;
 
   // ---- binning + compositing for a given pair capacity (D <= cap slots; [D,cap) are padding) ----
-  auto run_binning_and_render = [&](uint32_t cap) -> int {
+  auto run_binning_and_render = [&](uint32_t cap, const std::function<int()>* after_scan) -> int {
     size_t bin_bytes;
     carve_binning(nullptr, cap, tile_bits, &bin_bytes);
     char* bin_p = grow(binning, bin_bytes, "binning");
     if (!bin_p && bin_bytes) return B200GS_ERR_ALLOC;
     BinBuf bb = carve_binning(bin_p, cap, tile_bits, nullptr);
     int rc2;
-    if ((rc2 = check_cuda(cudaMemsetAsync(ib.ranges, 0, sizeof(uint2) * (size_t)num_tiles, st), "clear ranges")))
+    // global-sort pipeline: the ranges pass only writes bins that own pairs (the bucket scan writes every bin)
+    if ((!bucketed || P == 0) &&
+        (rc2 = check_cuda(cudaMemsetAsync(ib.ranges, 0, sizeof(uint2) * (size_t)num_tiles, st), "clear ranges")))
       return rc2;
     if (cap > 0 && bucketed) {
-      if ((rc2 = check_cuda(cudaMemsetAsync(gb.counters, 0, sizeof(uint32_t), st), "clear queue length"))) return rc2;
-      if ((rc2 = check_cuda(cudaMemsetAsync(ib.bin_cursor, 0, sizeof(uint32_t) * (size_t)num_tiles * BIN_STRIDE, st),
-                            "clear bin cursors")))
+      // queue lengths (large-footprint Gaussians, large segments) and window count; counters[1] = D is rewritten
+      if ((rc2 = check_cuda(cudaMemsetAsync(gb.counters, 0, 4 * sizeof(uint32_t), st), "clear queue lengths"))) return rc2;
+      if (!bin_pub_clean &&
+          (rc2 = check_cuda(cudaMemsetAsync(ib.bin_pub, 0, sizeof(unsigned long long) * (size_t)num_tiles, st),
+                            "clear look-back words")))
         return rc2;
       BucketArgs b2 = ba;
       b2.capacity = cap; b2.seg = bb.keys; b2.seg_alt = bb.keys_sorted; b2.vals_sorted = bb.vals_sorted;
+      b2.win_first = bb.win_first; b2.win_capacity = cap / BUCKET_WINDOW + BUCKET_BINS_MAX + 2; b2.big_segs = bb.big_segs;
+      {
+        StageTimer t(1, st);
+        launch_bucket_scan(b2, st);      // bucket starts, cursors, ranges clipped to `cap`, window table, D
+        bin_pub_clean = false;
+      }
+      if ((rc2 = debug_sync(prm, st, "bucket scan"))) return rc2;
+      if (after_scan && (rc2 = (*after_scan)())) return rc2;
       {
         StageTimer t(2, st);
-        launch_bin_scan(b2, st);            // per-bin ranges clipped to this capacity
-        launch_bucket_emit_sort_emit(b2, st);
+        launch_bucket_emit(b2, st);
       }
       if ((rc2 = debug_sync(prm, st, "emit pairs"))) return rc2;
       {
         StageTimer t(3, st);
-        launch_bucket_emit_sort_sort(b2, st);
+        launch_bucket_sort(b2, st);
       }
-      if ((rc2 = debug_sync(prm, st, "bin sort"))) return rc2;
+      if ((rc2 = debug_sync(prm, st, "bucket sort"))) return rc2;
     } else if (cap > 0) {
       if ((rc2 = check_cuda(cudaMemsetAsync(gb.counters, 0, 32 * sizeof(uint32_t), st), "clear counters"))) return rc2;
       const bool coop = use_coop_sort(cap);
@@ -534,15 +567,17 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
   };
 
   uint32_t D = 0;
-  const int64_t hint = prm->pair_capacity_hint;
-  if (P > 0 && hint > 0 && hint < (int64_t)0x7fffffff && (prm->flags & B200GS_DEFER_PAIR_CHECK)) {
+  const int64_t hint = hint_cap;
+  if (P > 0 && hint > 0 && (prm->flags & B200GS_DEFER_PAIR_CHECK)) {
     // Deferred check: D goes straight to the caller's pinned word; the host never waits here.
-    if ((rc = check_cuda(cudaMemcpyAsync(num_rendered, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st),
-                         "queue num_rendered copy (deferred)")))
-      return rc;
-    return run_binning_and_render((uint32_t)hint);
+    const std::function<int()> queue_copy = [&]() -> int {
+      return check_cuda(cudaMemcpyAsync(num_rendered, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st),
+                        "queue num_rendered copy (deferred)");
+    };
+    if (!bucketed && (rc = queue_copy())) return rc;      // global sort: D is known since the scan over Gaussians
+    return run_binning_and_render((uint32_t)hint, bucketed ? &queue_copy : nullptr);
   }
-  if (P > 0 && hint > 0 && hint < (int64_t)0x7fffffff) {
+  if (P > 0 && hint > 0) {
     // Speculative path: D stays on the device.  Its copy to pinned host memory is queued, the rest
     // of the frame is launched for `hint` pair slots, and only then does the host wait for the copy
     // (an event early in the stream) -- the GPU never idles while the host learns D.
@@ -550,16 +585,20 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
     if (!host_d) return B200GS_ERR_ALLOC;
     cudaEvent_t ev;
     if ((rc = check_cuda(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event create"))) return rc;
-    rc = check_cuda(cudaMemcpyAsync(host_d, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st),
-                    "queue num_rendered copy");
-    if (!rc) rc = check_cuda(cudaEventRecord(ev, st), "event record");
-    if (!rc) rc = run_binning_and_render((uint32_t)hint);
+    const std::function<int()> queue_copy = [&]() -> int {
+      int r = check_cuda(cudaMemcpyAsync(host_d, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st),
+                         "queue num_rendered copy");
+      if (!r) r = check_cuda(cudaEventRecord(ev, st), "event record");
+      return r;
+    };
+    if (!bucketed) rc = queue_copy();
+    if (!rc) rc = run_binning_and_render((uint32_t)hint, bucketed ? &queue_copy : nullptr);
     if (!rc) rc = check_cuda(cudaEventSynchronize(ev), "wait num_rendered");
     cudaEventDestroy(ev);
     if (rc) return rc;
     D = *host_d;
     *num_rendered = (int32_t)D;
-    if ((int64_t)D > hint) return run_binning_and_render(D);   // hint too small: redo exactly
+    if ((int64_t)D > hint) return run_binning_and_render(D, nullptr);   // hint too small: redo exactly
     return 0;
   }
   if (P > 0) {
@@ -569,7 +608,7 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
     if ((rc = check_cuda(cudaStreamSynchronize(st), "sync num_rendered"))) return rc;
   }
   *num_rendered = (int32_t)D;
-  return run_binning_and_render(D);
+  return run_binning_and_render(D, nullptr);
 }
 
 int b200gs_backward(const B200GSParams* prm, const float* bg, const float* viewmatrix,

@@ -1,27 +1,34 @@
-// bucket.cu -- bucketed binning: per-bin pair lists without a global sort.
+// bucket.cu -- depth-sliced bucket binning: per-bin, depth-ordered pair lists without a global sort.
 //
-// Replaces rows a4 InclusiveSum, a5 duplicateWithKeys, a6 SortPairs and
-// a7 identifyTileRanges of the public algorithm -- same result (every bin's Gaussian ids in
-// (depth bits, index) order, which is the order a stable radix sort of (bin << 32 | depth) keys
-// emitted in index order produces), different route.  The global-sort pipeline (binning.cu,
-// coopsort.cu) is latency-bound on B200: 0.8 M pairs are 9 MB, yet scan + emit + 5 onesweep passes +
-// ranges take 0.17 ms of a 0.39 ms C3 frame in 16 dependent launches whose decoupled look-back chains
-// cannot be hidden.  Here:
+// Replaces rows a4 InclusiveSum, a5 duplicateWithKeys, a6 SortPairs and a7 identifyTileRanges
+// of the public algorithm -- same result (every bin's Gaussian ids in (depth bits, index) order, which is the
+// order a stable radix sort of (bin << 32 | depth) keys emitted in index order produces), different route.
+// The global-sort pipeline (binning.cu: library scan + onesweep passes) is latency-bound on B200: 0.55 M pairs
+// are 4 MB, yet scan + emit + 4 passes + ranges take 0.14 ms of a 0.36 ms C3 frame in 13 dependent launches.
 //
-//   k_project      counts pairs per bin while it computes the spans (one RED per pair; counters
-//                  sit 256 B apart so the L2 atomic units never serialise two bins);
-//   k_bin_scan     one CTA: exclusive scan of the <= few thousand bin counts -> bin_base[], the
-//                  per-bin [start,end) ranges the compositing kernels read, and D;
-//   k_emit_bucket  appends (depth bits << 32 | id) to the bin's segment through a per-bin cursor
-//                  (order inside a segment is arbitrary);
-//   k_bin_sort     ONE launch, one CTA per bin: stable LSD radix sort of the segment on the depth
-//                  word, four 8-bit passes over L2-resident ping-pong buffers, ranks from
-//                  __match_any_sync multi-splits and per-warp shared-memory histograms.  Depth ties
-//                  (rare: equal fp32 view depths inside one bin) are put in index order afterwards --
-//                  short runs by insertion, long runs by re-sorting the bin on the full 64-bit key.
+// A pair's BUCKET is (bin, depth slice), slice = min(((depth bits - near-plane bits) >> slice_shift), S - 1):
+// the IEEE bits of a positive float grow with the float, so the slices cut the depth axis into S monotone
+// (logarithmic: 2^23 codes per octave, 16 octaves from the near plane) intervals, and the concatenation of a
+// bin's buckets in slice order is depth-ordered as soon as every bucket is.  S ~ 512 k / bins (8192 slices of
+// 0.14 % depth each at 1080p with 256-px bins), so a bucket holds about a dozen pairs.
 //
-// Five launches, no scan over Gaussians, no padding of a speculative capacity, no ranges pass; every
-// bin is sorted concurrently, so the stage is bound by four L2 round trips, not by the pair count.
+//   k_project        counts pairs per bucket while it computes the spans (one RED per pair);
+//   k_bucket_scan    one CTA per bin: exclusive scan of the bin's S counters, bin offsets by a decoupled look-back
+//                    over the lower bins -> absolute bucket starts (also the append cursors), the per-bin
+//                    [start,end) ranges the compositing kernels read, D, and the WINDOW table: a bin's list is cut
+//                    every BUCKET_WINDOW pairs at the next bucket boundary, window k starts at the first bucket
+//                    whose start is >= k * BUCKET_WINDOW -- equal work per sorter whatever the depth histogram;
+//   k_emit_bucket    appends ((depth bits - near bits) << 32 | id) to the pair's bucket through its cursor
+//                    (order inside a bucket is arbitrary; the sort key is a total order, so the result is
+//                    deterministic);
+//   k_bucket_sort    one warp per window: its buckets are contiguous in memory and ordered by slice, so sorting
+//                    their union on the 64-bit key is exactly the (depth, index) order; up to 512 keys in
+//                    registers, bitonic network with shuffles for the cross-lane stages.  A window that holds a
+//                    larger bucket (a wall that faces the camera puts a whole bin at one depth) is queued for
+//   k_bucket_sort_big  one CTA per queued segment: LSD radix passes over the key digits that actually differ
+//                    inside the segment, L2-resident ping-pong.
+//
+// Five launches, no scan over Gaussians, no padding of a speculative capacity, no ranges pass, no tie repair.
 #include "common.cuh"
 #include "kernels.cuh"
 #include "spans.cuh"
@@ -29,40 +36,108 @@
 
 namespace b200gs {
 
-// ---- k_bin_scan ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_bin_scan(BucketArgs a) {
+// ---- k_bucket_scan --------------------------------------------------------------------------------
+// One CTA per bin.  bin_pub[bin] = valid bit | windows << 32 | pairs, published once the bin's own scan is done;
+// a bin's offsets are the sums over the lower bins (CTAs are dispatched in index order, so a CTA only ever waits
+// for CTAs that are already running or done -- the usual decoupled look-back argument).
+constexpr int SCAN_THREADS = 1024;
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_bucket_scan(BucketArgs a) {
   __shared__ uint32_t s_warp[32];
-  __shared__ uint32_t s_carry;
+  __shared__ uint32_t s_off[3];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_carry = 0;
+  const uint32_t bin = blockIdx.x;
+  const uint32_t S = 1u << a.slices_log2;
+  const uint32_t per = S >= 8 * SCAN_THREADS ? 8u : 4u;          // counters per thread (S <= 8192)
+  const uint32_t b_first = bin * S + (uint32_t)tid * per;        // global index of the thread's first bucket
+  const bool active = (uint32_t)tid * per < S;
+  uint32_t c[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) c[k] = 0u;
+  if (active) {
+    const uint4 v0 = __ldcg(reinterpret_cast<const uint4*>(a.bucket_count + b_first));
+    c[0] = v0.x; c[1] = v0.y; c[2] = v0.z; c[3] = v0.w;
+    if (per == 8u) {
+      const uint4 v1 = __ldcg(reinterpret_cast<const uint4*>(a.bucket_count + b_first + 4));
+      c[4] = v1.x; c[5] = v1.y; c[6] = v1.z; c[7] = v1.w;
+    }
+  }
+  uint32_t sum = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) sum += c[k];
+  uint32_t incl = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
   __syncthreads();
-  for (uint32_t b0 = 0; b0 < a.num_bins; b0 += 1024) {
-    const uint32_t b = b0 + tid;
-    const uint32_t c = b < a.num_bins ? a.bin_count[(size_t)b * BIN_STRIDE] : 0u;
-    uint32_t incl = c;
+  if (warp == 0) {
+    const uint32_t w = s_warp[lane];
+    uint32_t wi = w;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += t;
+      const uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+      if (lane >= d) wi += t;
     }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    uint32_t wp = 0;
-    for (int w = 0; w < warp; w++) wp += s_warp[w];
-    const uint32_t carry = s_carry;
-    const uint32_t base = carry + wp + incl - c;
-    if (b < a.num_bins) {
-      a.bin_base[b] = base;
-      // a bin that does not fit the pair capacity is left empty: the host learns D > capacity and
-      // redoes the stage, and until then no kernel may index past the buffers
-      const bool fits = (uint64_t)base + c <= (uint64_t)a.capacity;
-      a.ranges[b] = fits ? make_uint2(base, base + c) : make_uint2(0u, 0u);
+    s_warp[lane] = wi - w;                                   // exclusive prefix of the warp totals
+    const uint32_t bin_total = __shfl_sync(0xffffffffu, wi, 31);
+    const uint32_t nwin = (bin_total + BUCKET_WINDOW - 1) / BUCKET_WINDOW;
+    volatile unsigned long long* pub = reinterpret_cast<volatile unsigned long long*>(a.bin_pub);
+    if (lane == 0) pub[bin] = (1ull << 63) | ((unsigned long long)nwin << 32) | bin_total;
+    // look-back over the lower bins
+    uint32_t off = 0, woff = 0;
+    for (uint32_t j = lane; j < bin; j += 32) {
+      unsigned long long v;
+      do { v = pub[j]; } while (!(v >> 63));
+      off += (uint32_t)v;
+      woff += (uint32_t)(v >> 32) & 0x7FFFFFFFu;
     }
-    __syncthreads();
-    if (tid == 1023) s_carry = carry + wp + incl;
-    __syncthreads();
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      off += __shfl_xor_sync(0xffffffffu, off, d);
+      woff += __shfl_xor_sync(0xffffffffu, woff, d);
+    }
+    if (lane == 0) { s_off[0] = off; s_off[1] = woff; s_off[2] = bin_total; }
   }
-  if (tid == 0) *a.total = s_carry;   // D
+  __syncthreads();
+  const uint32_t off = s_off[0], woff = s_off[1], bin_total = s_off[2];
+  const uint32_t nwin = (bin_total + BUCKET_WINDOW - 1) / BUCKET_WINDOW;
+  if (active) {
+    uint32_t lp = s_warp[warp] + incl - sum;                 // local (in-bin) start of the thread's first bucket
+    uint32_t o[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      o[k] = off + lp;
+      // window table: bucket b = [lp, lp + c) makes b + 1 the first bucket at or behind every window boundary
+      // W k in (lp, lp + c]; the boundary at the very end of the bin belongs to the next bin's first window
+      if (a.win_first && c[k] && (uint32_t)k < per) {
+        const uint32_t k1 = min((lp + c[k]) / BUCKET_WINDOW, nwin ? nwin - 1u : 0u);
+        for (uint32_t w = lp / BUCKET_WINDOW + 1u; w <= k1; w++)
+          if (woff + w < a.win_capacity) a.win_first[woff + w] = b_first + k + 1u;     // (more pairs than capacity)
+      }
+      lp += c[k];
+    }
+    *reinterpret_cast<uint4*>(a.bucket_base + b_first) = make_uint4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<uint4*>(a.bucket_cursor + b_first) = make_uint4(o[0], o[1], o[2], o[3]);
+    if (per == 8u) {
+      *reinterpret_cast<uint4*>(a.bucket_base + b_first + 4) = make_uint4(o[4], o[5], o[6], o[7]);
+      *reinterpret_cast<uint4*>(a.bucket_cursor + b_first + 4) = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+  }
+  if (tid == 0) {
+    if (a.win_first && nwin && woff < a.win_capacity) a.win_first[woff] = bin * S;
+    // A bin that does not fit the pair capacity is left empty: the caller learns D > capacity and redoes the
+    // stage, and until then no kernel may index past the buffers.
+    a.ranges[bin] = (off + bin_total <= a.capacity) ? make_uint2(off, off + bin_total) : make_uint2(0u, 0u);
+    if (bin == a.num_bins - 1) {
+      a.bucket_base[a.num_bins * S] = off + bin_total;
+      *a.total = off + bin_total;                            // D
+      *a.total_windows = woff + nwin;
+      if (a.win_first && woff + nwin < a.win_capacity) a.win_first[woff + nwin] = a.num_bins * S;
+    }
+  }
 }
 
 // ---- k_emit_bucket / k_emit_bucket_big ------------------------------------------------------------
@@ -70,15 +145,21 @@ constexpr uint32_t BUCKET_BIG_THRESHOLD = 12;   // bins; above this a whole warp
 constexpr int EMIT_WARPS = 8;
 constexpr int EMIT_STAGE = 32 * BUCKET_BIG_THRESHOLD;   // staged (bin, owner lane) entries per warp
 
-__device__ __forceinline__ void emit_one(const BucketArgs& a, uint32_t bin, uint64_t key) {
-  const uint32_t slot = __ldg(a.bin_base + bin) + atomicAdd(a.bin_cursor + (size_t)bin * BIN_STRIDE, 1u);
+__device__ __forceinline__ uint32_t rel_depth(const BucketArgs& a, uint32_t depth_bits) {
+  return depth_bits > a.near_bits ? depth_bits - a.near_bits : 0u;
+}
+__device__ __forceinline__ uint32_t slice_of(const BucketArgs& a, uint32_t rel) {
+  return min(rel >> a.slice_shift, (1u << a.slices_log2) - 1u);
+}
+__device__ __forceinline__ void emit_one(const BucketArgs& a, uint32_t bin, uint32_t slice, uint64_t key) {
+  const uint32_t slot = atomicAdd(a.bucket_cursor + ((bin << a.slices_log2) + slice), 1u);
   if (slot < a.capacity) a.seg[slot] = key;
 }
 
-// A cursor increment is an L2 round trip (~0.5 us) and a Gaussian's bins depend on nothing, so a lane
-// that walked its own bins one atomic after the other would serialise up to 12 round trips while most
-// lanes of the warp (culled Gaussians) idle.  Instead every lane first STAGES its bins in shared memory
-// (no memory traffic), then the warp drains the staged list 32 pairs per round, one atomic per lane.
+// A cursor increment is an L2 round trip (~0.5 us) and a Gaussian's bins depend on nothing, so a lane that
+// walked its own bins one atomic after the other would serialise up to 12 round trips while most lanes of the
+// warp (culled Gaussians) idle.  Instead every lane first STAGES its bins in shared memory (no memory
+// traffic), then the warp drains the staged list 32 pairs per round, one atomic per lane.
 __global__ void __launch_bounds__(32 * EMIT_WARPS) k_emit_bucket(BucketArgs a) {
   __shared__ uint32_t stage[EMIT_WARPS][EMIT_STAGE];
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -96,9 +177,9 @@ __global__ void __launch_bounds__(32 * EMIT_WARPS) k_emit_bucket(BucketArgs a) {
   }
   const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
   if (total == 0) return;
-  uint32_t depth = 0;
+  uint32_t rel = 0;
   if (n) {
-    depth = a.depth_key[r];
+    rel = rel_depth(a, a.depth_key[r]);
     const float4 q0 = a.rec[(size_t)r * REC_F4], q1 = a.rec[(size_t)r * REC_F4 + 1];
     const TileRect rect = bin_rect(reference_rect(q0.x, q0.y, a.radii[r], a.gx, a.gy), a.bin_shift);
     SpanCtx s;
@@ -118,10 +199,10 @@ __global__ void __launch_bounds__(32 * EMIT_WARPS) k_emit_bucket(BucketArgs a) {
     const uint32_t k = k0 + lane;
     const uint32_t e = (k < total) ? stage[warp][k] : 0u;
     const int owner = (int)(e >> 16);
-    const uint32_t od = __shfl_sync(0xffffffffu, depth, owner);
+    const uint32_t orel = __shfl_sync(0xffffffffu, rel, owner);
     const uint32_t oid = (uint32_t)(r - lane + owner);
     const uint32_t bin = e & 0xFFFFu;
-    if (k < total && bin != 0xFFFFu) emit_one(a, bin, ((uint64_t)od << 32) | oid);
+    if (k < total && bin != 0xFFFFu) emit_one(a, bin, slice_of(a, orel), ((uint64_t)orel << 32) | oid);
   }
 }
 
@@ -134,7 +215,9 @@ __global__ void __launch_bounds__(256) k_emit_bucket_big(BucketArgs a) {
   for (uint32_t w = warp_global; w < count; w += nwarps) {
     const uint32_t g = a.big_queue[w];
     const float4 q0 = a.rec[(size_t)g * REC_F4], q1 = a.rec[(size_t)g * REC_F4 + 1];
-    const uint64_t key = ((uint64_t)a.depth_key[g] << 32) | g;
+    const uint32_t rel = rel_depth(a, a.depth_key[g]);
+    const uint32_t slice = slice_of(a, rel);
+    const uint64_t key = ((uint64_t)rel << 32) | g;
     const TileRect rect = bin_rect(reference_rect(q0.x, q0.y, a.radii[g], a.gx, a.gy), a.bin_shift);
     SpanCtx s;
     if (!span_setup(s, q0.x, q0.y, q0.z, q0.w, q1.x, q1.z, rect, a.bin_shift)) continue;
@@ -145,13 +228,93 @@ __global__ void __launch_bounds__(256) k_emit_bucket_big(BucketArgs a) {
       const int rows = min(32, s.ty1 - y_base);
       for (int i = 0; i < rows; i++) {
         const int c0_i = __shfl_sync(0xffffffffu, c0, i), c1_i = __shfl_sync(0xffffffffu, c1, i);
-        for (int tx = c0_i + lane; tx < c1_i; tx += 32) emit_one(a, (uint32_t)((y_base + i) * a.gbx + tx), key);
+        for (int tx = c0_i + lane; tx < c1_i; tx += 32) emit_one(a, (uint32_t)((y_base + i) * a.gbx + tx), slice, key);
       }
     }
   }
 }
 
-// ---- k_bin_sort (BinSortShared / bin_sort_pass: binsort.cuh) ---------------------------------------
+// ---- k_bucket_sort: one warp per bucket, keys in registers ---------------------------------------------
+// Element i of the bucket lives in register i / 32 of lane i % 32.  Bitonic network: partners 32 or more
+// apart are two registers of the same lane, closer partners are exchanged with shuffles.
+template <int K>
+__device__ __forceinline__ void warp_bitonic_sort(uint64_t (&key)[K], int lane) {
+  constexpr int N = 32 * K;
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+        const int jr = j >> 5;
+#pragma unroll
+        for (int r = 0; r < K; r++) {
+          if ((r & jr) == 0) {
+            const bool asc = (((r << 5) & k) == 0);   // bit k of the element index: k >= 64 here, a register bit
+            const uint64_t lo = key[r] < key[r | jr] ? key[r] : key[r | jr];
+            const uint64_t hi = key[r] < key[r | jr] ? key[r | jr] : key[r];
+            key[r] = asc ? lo : hi;
+            key[r | jr] = asc ? hi : lo;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < K; r++) {
+          const uint64_t other = __shfl_xor_sync(0xffffffffu, key[r], j);
+          const int i = (r << 5) | lane;
+          const bool asc = (i & k) == 0;
+          const bool lower = (lane & j) == 0;           // this lane keeps the smaller key when ascending
+          const bool take_min = (asc == lower);
+          const bool other_less = other < key[r];
+          key[r] = (take_min == other_less) ? other : key[r];
+        }
+      }
+    }
+  }
+}
+
+template <int K>
+__device__ __forceinline__ void sort_bucket_in_registers(const uint64_t* __restrict__ seg, uint32_t* __restrict__ out,
+                                                         uint32_t n, int lane) {
+  uint64_t key[K];
+#pragma unroll
+  for (int r = 0; r < K; r++) {
+    const uint32_t i = (uint32_t)(r * 32 + lane);
+    key[r] = i < n ? __ldcg(seg + i) : ~0ull;          // padding sorts last
+  }
+  warp_bitonic_sort<K>(key, lane);
+#pragma unroll
+  for (int r = 0; r < K; r++) {
+    const uint32_t i = (uint32_t)(r * 32 + lane);
+    if (i < n) out[i] = (uint32_t)key[r];
+  }
+}
+
+constexpr uint32_t WARP_SORT_MAX = 512;
+constexpr int SORT_WARPS = 8;
+
+__global__ void __launch_bounds__(32 * SORT_WARPS) k_bucket_sort(BucketArgs a) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t w = blockIdx.x * SORT_WARPS + (threadIdx.x >> 5);
+  if (w >= __ldcg(a.total_windows) || w + 1 >= a.win_capacity) return;
+  const uint32_t b0 = __ldcg(a.win_first + w), b1 = __ldcg(a.win_first + w + 1);
+  const uint32_t s = __ldcg(a.bucket_base + b0), e = __ldcg(a.bucket_base + b1);
+  const uint32_t n = e - s;
+  if (n == 0 || e > a.capacity) return;        // over capacity: the frame is redone, never index past the buffers
+  const uint64_t* seg = a.seg + s;
+  uint32_t* out = a.vals_sorted + s;
+  if (n > WARP_SORT_MAX) {
+    if (lane == 0) a.big_segs[atomicAdd(a.big_seg_count, 1u)] = make_uint2(s, n);
+    return;
+  }
+  if (n == 1) { if (lane == 0) out[0] = (uint32_t)__ldcg(seg); }
+  else if (n <= 32) sort_bucket_in_registers<1>(seg, out, n, lane);
+  else if (n <= 64) sort_bucket_in_registers<2>(seg, out, n, lane);
+  else if (n <= 128) sort_bucket_in_registers<4>(seg, out, n, lane);
+  else if (n <= 256) sort_bucket_in_registers<8>(seg, out, n, lane);
+  else sort_bucket_in_registers<16>(seg, out, n, lane);
+}
+
+// ---- k_bucket_sort_big (BinSortShared / bin_sort_pass: binsort.cuh) -----------------------------------
 // Same pass for segments of at most K*32*BS_WARPS elements, K keys per thread: the keys of a pass are
 // fetched with ONE batch of independent loads and stay in registers between the ranking and the
 // scatter, so a pass costs one L2 round trip instead of one per 32 elements.  Peer masks come from
@@ -229,75 +392,72 @@ __device__ __forceinline__ void bin_sort_pass_regs(BinSortShared& sh, const uint
   __syncthreads();
 }
 
-// K = 0: any length (keys re-read per 32-element group); K > 0: segments of (lo, K*32*BS_WARPS] elements.
-// One launch per class; a CTA whose bin belongs to another class exits at once, so small bins are not
-// sorted by a kernel that carries the register budget of the large ones.
-template <int K>
-__global__ void __launch_bounds__(BS_THREADS) k_bin_sort(BucketArgs a, uint32_t lo, uint32_t hi) {
+// One CTA per queued segment (a window that holds a bucket of more than a few hundred pairs).  LSD radix passes
+// over the 8-bit digits of the 64-bit key that are not constant over the segment: inside one bucket only the index
+// bits and the low slice_shift depth bits differ.
+__global__ void __launch_bounds__(BS_THREADS) k_bucket_sort_big(BucketArgs a) {
   __shared__ BinSortShared sh;
-  const uint32_t b = blockIdx.x;
-  const uint2 range = a.ranges[b];
-  const uint32_t n = range.y - range.x;
-  if (n <= lo || n > hi) return;
-  uint64_t* A = a.seg + range.x;
-  uint64_t* B = a.seg_alt + range.x;
-  const int tid = threadIdx.x;
-  if (tid == 0) sh.long_run = 0u;
-  auto pass = [&](const uint64_t* src, uint64_t* dst, int shift) {
-    if constexpr (K == 0) bin_sort_pass(sh, src, dst, n, shift);
-    else bin_sort_pass_regs<K>(sh, src, dst, n, shift);
-  };
-  // four passes over the depth word: A -> B -> A -> B -> A
-  for (int p = 0; p < 4; p++) pass((p & 1) ? B : A, (p & 1) ? A : B, 32 + 8 * p);
-  uint64_t* F = A;
-  // depth ties: heads of equal-depth runs put their run in index order
-  for (uint32_t i = tid; i + 1 < n; i += BS_THREADS) {
-    const uint32_t d = (uint32_t)(__ldcg(F + i) >> 32);
-    if ((uint32_t)(__ldcg(F + i + 1) >> 32) != d) continue;
-    if (i > 0 && (uint32_t)(__ldcg(F + i - 1) >> 32) == d) continue;   // not the head
-    uint32_t e = i + 2;
-    while (e < n && e - i <= BS_TIE_INSERTION_MAX && (uint32_t)(__ldcg(F + e) >> 32) == d) e++;
-    if (e - i > BS_TIE_INSERTION_MAX) { sh.long_run = 1u; continue; }
-    for (uint32_t x = i + 1; x < e; x++) {      // insertion sort of [i, e) on the full key
-      const uint64_t k = __ldcg(F + x);
-      uint32_t y = x;
-      while (y > i && __ldcg(F + y - 1) > k) { F[y] = __ldcg(F + y - 1); y--; }
-      F[y] = k;
+  __shared__ unsigned long long s_or, s_and;
+  const uint32_t count = *a.big_seg_count;
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (uint32_t q = blockIdx.x; q < count; q += gridDim.x) {
+    const uint2 sg = a.big_segs[q];
+    const uint32_t s = sg.x, n = sg.y;
+    uint64_t* A = a.seg + s;
+    uint64_t* B = a.seg_alt + s;
+    if (tid == 0) { s_or = 0ull; s_and = ~0ull; }
+    __syncthreads();
+    unsigned long long o = 0ull, an = ~0ull;
+    for (uint32_t i = tid; i < n; i += BS_THREADS) {
+      const unsigned long long k = __ldcg(A + i);
+      o |= k; an &= k;
     }
-  }
-  __syncthreads();
-  if (sh.long_run) {
-    // many equal depths (e.g. a fronto-parallel planar scene): sort the bin on the full 64-bit key,
-    // index digits first (stable LSD), then the depth word again
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      o |= __shfl_xor_sync(0xffffffffu, o, d);
+      an &= __shfl_xor_sync(0xffffffffu, an, d);
+    }
+    if (lane == 0) { atomicOr(&s_or, o); atomicAnd(&s_and, an); }
+    __syncthreads();
+    const unsigned long long varying = s_or ^ s_and;
+    __syncthreads();
     int passes = 0;
-    for (int s = 0; s < a.id_bits; s += 8, passes++) pass((passes & 1) ? B : A, (passes & 1) ? A : B, s);
-    for (int p = 0; p < 4; p++, passes++) pass((passes & 1) ? B : A, (passes & 1) ? A : B, 32 + 8 * p);
-    F = (passes & 1) ? B : A;
+    for (int sft = 0; sft < 64; sft += 8) {
+      if (!((varying >> sft) & 0xFFull)) continue;          // CTA-uniform: this digit is the same in every key
+      const uint64_t* src = (passes & 1) ? B : A;
+      uint64_t* dst = (passes & 1) ? A : B;
+      if (n <= 2 * 32 * BS_WARPS) bin_sort_pass_regs<2>(sh, src, dst, n, sft);
+      else if (n <= 8 * 32 * BS_WARPS) bin_sort_pass_regs<8>(sh, src, dst, n, sft);
+      else if (n <= 24 * 32 * BS_WARPS) bin_sort_pass_regs<24>(sh, src, dst, n, sft);
+      else bin_sort_pass(sh, src, dst, n, sft);
+      passes++;
+    }
+    const uint64_t* F = (passes & 1) ? B : A;
+    uint32_t* out = a.vals_sorted + s;
+    for (uint32_t i = tid; i < n; i += BS_THREADS) out[i] = (uint32_t)__ldcg(F + i);
+    __syncthreads();
   }
-  uint32_t* out = a.vals_sorted + range.x;
-  for (uint32_t i = tid; i < n; i += BS_THREADS) out[i] = (uint32_t)__ldcg(F + i);
 }
 
 // ---- host ---------------------------------------------------------------------------------------
-void launch_bin_scan(const BucketArgs& a, cudaStream_t st) {
-  k_bin_scan<<<1, 1024, 0, st>>>(a);
+void launch_bucket_scan(const BucketArgs& a, cudaStream_t st) {
+  k_bucket_scan<<<a.num_bins, SCAN_THREADS, 0, st>>>(a);
   count_launch();
 }
 
-void launch_bucket_emit_sort_emit(const BucketArgs& a, cudaStream_t st) {
+void launch_bucket_emit(const BucketArgs& a, cudaStream_t st) {
   if (a.P == 0 || a.capacity == 0) return;
   k_emit_bucket<<<(a.P + 255) / 256, 256, 0, st>>>(a);
   k_emit_bucket_big<<<148 * 2, 256, 0, st>>>(a);
   count_launch(2);
 }
 
-void launch_bucket_emit_sort_sort(const BucketArgs& a, cudaStream_t st) {
+void launch_bucket_sort(const BucketArgs& a, cudaStream_t st) {
   if (a.P == 0 || a.capacity == 0) return;
-  constexpr uint32_t SMALL = 8 * 32 * BS_WARPS, LARGE = 24 * 32 * BS_WARPS;   // 4096, 12288
-  k_bin_sort<8><<<a.num_bins, BS_THREADS, 0, st>>>(a, 0u, SMALL);
-  k_bin_sort<24><<<a.num_bins, BS_THREADS, 0, st>>>(a, SMALL, LARGE);
-  k_bin_sort<0><<<a.num_bins, BS_THREADS, 0, st>>>(a, LARGE, 0xFFFFFFFFu);
-  count_launch(3);
+  const uint32_t max_windows = a.capacity / BUCKET_WINDOW + a.num_bins;     // sum over bins of ceil(pairs / W)
+  k_bucket_sort<<<(max_windows + SORT_WARPS - 1) / SORT_WARPS, 32 * SORT_WARPS, 0, st>>>(a);
+  k_bucket_sort_big<<<148 * 2, BS_THREADS, 0, st>>>(a);
+  count_launch(2);
 }
 
 }  // namespace b200gs

@@ -53,6 +53,8 @@ struct BinBuf {
   uint64_t* keys;        // [D] (bin << 32) | depth bits, emission (index) order
   uint32_t* vals;        // [D] Gaussian ids
   uint32_t* coop_hist;   // rotating digit histograms of the cooperative sort
+  uint32_t* win_first;   // [D / BUCKET_WINDOW + BUCKET_BINS_MAX + 2] bucketed binning: first bucket of every sort window
+  uint2* big_segs;       // [D / 512 + 2] bucketed binning: segments queued for the one-CTA sort
   char* cub_temp;
   size_t cub_temp_bytes;
 };
@@ -61,11 +63,11 @@ struct ImgBuf {
   uint2* ranges;        // [tiles] [start,end) into the slab
   float4* pix;          // [H*W] {accumulated r,g,b (no background), final transmittance}
   uint32_t* n_contrib;  // [H*W] list position behind which nothing contributes to the pixel
-  // bucketed binning (sized for the finest bins = 16-px tiles, so the layout never depends on the bin
-  // size): per-bin pair counters and append cursors, 256 B apart; per-bin segment starts
-  uint32_t* bin_count;  // [tiles * 64]
-  uint32_t* bin_cursor; // [tiles * 64]
-  uint32_t* bin_base;   // [tiles]
+  // bucketed binning (bucket.cu): fixed-size tables, so the layout never depends on the bin size
+  unsigned long long* bin_pub;   // [BUCKET_BINS_MAX] look-back words of the bucket scan -- directly in front of
+  uint32_t* bucket_count;   // [BUCKETS_MAX] pairs per (bin, depth slice) bucket (one memset clears both)
+  uint32_t* bucket_base;    // [BUCKETS_MAX + 4] exclusive scan (+ total)
+  uint32_t* bucket_cursor;  // [BUCKETS_MAX]
 };
 
 // ---- small math helpers ---------------------------------------------------------------------

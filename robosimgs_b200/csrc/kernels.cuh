@@ -4,12 +4,18 @@
 
 namespace b200gs {
 
-constexpr int BIN_STRIDE = 64;   // words between per-bin counters (256 B: one L2 atomic unit per bin)
+// bucketed binning (bucket.cu): (bin, depth slice) buckets, at most BUCKET_BINS_MAX bins of 4..8192 slices
+constexpr uint32_t BUCKETS_MAX = 512 * 1024;
+constexpr uint32_t BUCKET_BINS_MAX = 1024;
+constexpr int BUCKET_SLICES_LOG2_MAX = 13;
+constexpr uint32_t BUCKET_WINDOW = 192;   // pairs per sorter warp (cut at the next bucket boundary)
 
 struct ProjectArgs {
   int P, M, W, H, gx, gy, sh_vec, bin_shift;
   int gbx;               // bin grid width
-  uint32_t* bin_count;   // bucketed binning: per-bin pair counters (stride BIN_STRIDE), else nullptr
+  uint32_t* bucket_count;  // bucketed binning: per-(bin, depth slice) pair counters, else nullptr
+  int slices_log2, slice_shift;   // slice = min((depth bits - near_bits) >> slice_shift, 2^slices_log2 - 1)
+  uint32_t near_bits;
   float tanfovx, tanfovy, scale_modifier, near_plane;
   const float *means, *scales, *rots, *opac, *shs, *colors_precomp, *cov3d_precomp;
   const float *view, *proj, *campos;
@@ -39,16 +45,25 @@ struct EmitArgs {
 struct BucketArgs {
   int P, gx, gy, gbx, bin_shift;
   int id_bits;              // bits of the largest Gaussian index
+  int slices_log2, slice_shift;
+  uint32_t near_bits;       // IEEE bits of the near plane (origin of the depth slices)
   uint32_t num_bins, capacity;
   const uint32_t *tiles, *depth_key;
   const float4* rec;
   const int32_t* radii;
-  uint32_t *bin_count, *bin_cursor;   // stride BIN_STRIDE
-  uint32_t* bin_base;                 // [num_bins]
+  uint32_t* bucket_count;             // [num_bins << slices_log2] pairs per bucket (written by k_project)
+  uint32_t* bucket_base;              // [(num_bins << slices_log2) + 1] exclusive scan
+  uint32_t* bucket_cursor;            // [num_bins << slices_log2] append cursors (start at bucket_base)
   uint2* ranges;                      // [num_bins] per-bin [start,end) into vals_sorted
   uint32_t* total;                    // D
-  uint32_t *big_queue, *big_count;
-  uint64_t *seg, *seg_alt;            // [capacity] (depth bits << 32 | id), ping-pong
+  uint32_t *big_queue, *big_count;    // large-footprint Gaussians (emitted one warp each)
+  unsigned long long* bin_pub;        // [num_bins] look-back words of the scan (valid | windows << 32 | pairs), zeroed
+  uint32_t* win_first;                // [capacity / BUCKET_WINDOW + num_bins + 2] first bucket of every sort window
+  uint32_t win_capacity;              // entries of win_first
+  uint32_t* total_windows;
+  uint2* big_segs;                    // [capacity / 512 + 2] (start, length) of segments too large for the warp sort
+  uint32_t* big_seg_count;
+  uint64_t *seg, *seg_alt;            // [capacity] ((depth bits - near bits) << 32 | id), ping-pong
   uint32_t* vals_sorted;              // [capacity] Gaussian ids in (bin, depth, index) order
 };
 
@@ -148,9 +163,9 @@ void launch_photometric_loss_bwd(const float* a, const float* b, size_t n, float
                                  const float* upstream, float* g, cudaStream_t st);
 
 // bucket.cu: bucketed binning (per-bin lists without a global sort)
-void launch_bin_scan(const BucketArgs& a, cudaStream_t st);
-void launch_bucket_emit_sort_emit(const BucketArgs& a, cudaStream_t st);
-void launch_bucket_emit_sort_sort(const BucketArgs& a, cudaStream_t st);
+void launch_bucket_scan(const BucketArgs& a, cudaStream_t st);
+void launch_bucket_emit(const BucketArgs& a, cudaStream_t st);
+void launch_bucket_sort(const BucketArgs& a, cudaStream_t st);
 
 // train.cu: fused SSIM and multi-tensor Adam
 void launch_ssim_fwd(const float* img1, const float* img2, int C, int H, int W, float* maps, float* out_sum,

@@ -206,7 +206,13 @@ __global__ void __launch_bounds__(256, PROJECT_MIN_BLOCKS) k_project(ProjectArgs
         const float o = __ldg(a.opac + i);
         // 0.5*q <= thr  <=>  o*exp(-0.5 q) >= 1/255 ; slack keeps the test conservative
         const float thr = __logf(255.f * o) + 0.01f;
-        ntiles = (o > 0.f) ? count_tiles(px, py, A, B, C, thr, bin_rect(r, a.bin_shift), a.bin_shift, a.bin_count, a.gbx) : 0u;
+        uint32_t* cnt = nullptr;
+        if (a.bucket_count) {     // bucketed binning: the splat's depth slice of every bin it touches
+          const uint32_t db = __float_as_uint(vz);
+          const uint32_t rel = db > a.near_bits ? db - a.near_bits : 0u;
+          cnt = a.bucket_count + min(rel >> a.slice_shift, (1u << a.slices_log2) - 1u);
+        }
+        ntiles = (o > 0.f) ? count_tiles(px, py, A, B, C, thr, bin_rect(r, a.bin_shift), a.bin_shift, cnt, a.slices_log2, a.gbx) : 0u;
         if (ntiles > 0) {
           float rgb[3];
           uint32_t clampbits = 0;

@@ -114,10 +114,12 @@ __device__ __forceinline__ void row_span(const SpanCtx& s, const TileRect& r, in
   if (t1 > t0) { c0 = t0; c1 = t1; }
 }
 
-// Number of bins the splat touches.  With bin_count != nullptr (bucketed binning, bucket.cu) every
-// touched bin's pair counter is incremented as well: one RED per pair, counters BIN_STRIDE words apart.
+// Number of bins the splat touches.  With bucket_count != nullptr (bucketed binning, bucket.cu) the pair counter
+// of every touched bin's bucket is incremented as well (one RED per pair): bucket_count already points at the
+// splat's depth slice, the buckets of one bin are `bucket_stride` counters apart.
 __device__ __forceinline__ uint32_t count_tiles(float x, float y, float A, float B, float C, float thr,
-                                                const TileRect& r, int bin_shift, uint32_t* bin_count, int gbx) {
+                                                const TileRect& r, int bin_shift, uint32_t* bucket_count,
+                                                int bucket_stride_log2, int gbx) {
   SpanCtx s;
   if (!span_setup(s, x, y, A, B, C, thr, r, bin_shift)) return 0;
   uint32_t n = 0;
@@ -125,8 +127,8 @@ __device__ __forceinline__ uint32_t count_tiles(float x, float y, float A, float
     int c0, c1;
     row_span(s, r, ty, c0, c1);
     n += (uint32_t)(c1 - c0);
-    if (bin_count)
-      for (int tx = c0; tx < c1; tx++) atomicAdd(bin_count + (size_t)(ty * gbx + tx) * BIN_STRIDE, 1u);
+    if (bucket_count)
+      for (int tx = c0; tx < c1; tx++) atomicAdd(bucket_count + ((size_t)(ty * gbx + tx) << bucket_stride_log2), 1u);
   }
   return n;
 }

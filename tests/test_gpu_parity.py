@@ -525,3 +525,38 @@ def test_flat_input_layouts_and_forward_only_deferred_guard():
     assert frame.grad_fn is None and not frame.requires_grad
     assert ticket.ok()
     assert torch.equal(frame, color.detach())
+
+
+@pytest.mark.parametrize("P,spread", [(3000, 0.0005), (40000, 0.0005), (160000, 0.0), (60000, 0.6)])
+def test_bucket_sort_size_classes_match_the_global_sort(P, spread):
+    """Depth-sliced bucket binning (bucket.cu) against the library-sort pipeline, bit for bit, on walls that face the
+    camera -- nearly all pairs of a bin fall into one or two depth slices, so the buckets run through every size
+    class: the in-register warp sort (<= 512 keys), the one-CTA radix passes with keys in registers (<= 4096,
+    <= 12288) and the any-length passes; spread = 0 makes every depth bit-identical (pure index order), a wide
+    spread exercises many small buckets.  Both bin sizes (16 px: many bins, few slices; 128 px: the reverse)."""
+    from robosimgs_b200 import _cabi
+    from robosimgs_b200.cameras import camera_look_at
+    from robosimgs_b200.scenes import Scene
+    g = torch.Generator().manual_seed(P)
+    cam = camera_look_at((0.0, 0.0, 3.0), (0.0, 0.0, 0.0), (0, 1, 0), 50.0, 320, 256)
+    xy = torch.rand(P, 2, generator=g) * 3.0 - 1.5
+    z = (torch.rand(P, 1, generator=g) - 0.5) * spread
+    rgb = torch.rand(P, 1, 3, generator=g)
+    sc = Scene(torch.cat([xy, z], 1), (rgb - 0.5) / 0.28209479177387814, torch.rand(P, 1, generator=g) * 0.3 + 0.05,
+               torch.rand(P, 3, generator=g) * 0.03 + 0.01, torch.tensor([[1.0, 0, 0, 0]]).repeat(P, 1), 0)
+    try:
+        for shift in (0, 3):
+            _cabi.set_option("bin_shift", shift)
+            out = []
+            for binning in (1, 0):
+                _cabi.set_option("binning", binning)
+                _cabi.set_option("sort", 0)
+                _cabi.set_option("sort_keys", 64)
+                color, radii, _ = gpu_render(sc, cam, 0, bg=(0.1, 0.1, 0.1))
+                out.append(color)
+            assert np.array_equal(out[0], out[1]), (P, spread, shift)
+    finally:
+        _cabi.set_option("binning", -1)
+        _cabi.set_option("bin_shift", -1)
+        _cabi.set_option("sort", 1)
+        _cabi.set_option("sort_keys", 32)
