@@ -28,7 +28,7 @@
 //   k_bucket_sort_big  one CTA per queued segment: LSD radix passes over the key digits that actually differ
 //                    inside the segment, L2-resident ping-pong.
 //
-// Five launches, no scan over Gaussians, no padding of a speculative capacity, no ranges pass, no tie repair.
+// Four launches behind the projection kernel, no scan over Gaussians, no padding of a speculative capacity, no ranges pass, no tie repair.
 #include "common.cuh"
 #include "kernels.cuh"
 #include "spans.cuh"
@@ -165,10 +165,8 @@ __global__ void __launch_bounds__(32 * EMIT_WARPS) k_emit_bucket(BucketArgs a) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t n = (r < a.P) ? a.tiles[r] : 0u;
-  if (n > BUCKET_BIG_THRESHOLD) {
-    a.big_queue[atomicAdd(a.big_count, 1u)] = (uint32_t)r;
-    n = 0;
-  }
+  const uint32_t big_lanes = __ballot_sync(0xffffffffu, n > BUCKET_BIG_THRESHOLD);
+  if (n > BUCKET_BIG_THRESHOLD) n = 0;          // large footprints: emitted by the whole warp below
   uint32_t incl = n;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -176,7 +174,7 @@ __global__ void __launch_bounds__(32 * EMIT_WARPS) k_emit_bucket(BucketArgs a) {
     if (lane >= d) incl += t;
   }
   const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-  if (total == 0) return;
+  if (total == 0 && big_lanes == 0u) return;
   uint32_t rel = 0;
   if (n) {
     rel = rel_depth(a, a.depth_key[r]);
@@ -204,20 +202,14 @@ __global__ void __launch_bounds__(32 * EMIT_WARPS) k_emit_bucket(BucketArgs a) {
     const uint32_t bin = e & 0xFFFFu;
     if (k < total && bin != 0xFFFFu) emit_one(a, bin, slice_of(a, orel), ((uint64_t)orel << 32) | oid);
   }
-}
-
-// one warp per queued Gaussian: lanes take the bin rows, then the bins of each row, in parallel
-__global__ void __launch_bounds__(256) k_emit_bucket_big(BucketArgs a) {
-  const int lane = threadIdx.x & 31;
-  const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-  const uint32_t count = *a.big_count;
-  for (uint32_t w = warp_global; w < count; w += nwarps) {
-    const uint32_t g = a.big_queue[w];
+  // large footprints (a few screen-filling splats): one Gaussian at a time, lanes take the bin rows, then the bins of
+  // each row, in parallel -- so that one of them cannot serialise a lane for hundreds of atomics
+  for (uint32_t m = big_lanes; m; m &= m - 1u) {
+    const uint32_t g = (uint32_t)(r - lane) + (uint32_t)(__ffs(m) - 1);
     const float4 q0 = a.rec[(size_t)g * REC_F4], q1 = a.rec[(size_t)g * REC_F4 + 1];
-    const uint32_t rel = rel_depth(a, a.depth_key[g]);
-    const uint32_t slice = slice_of(a, rel);
-    const uint64_t key = ((uint64_t)rel << 32) | g;
+    const uint32_t grel = rel_depth(a, a.depth_key[g]);
+    const uint32_t slice = slice_of(a, grel);
+    const uint64_t key = ((uint64_t)grel << 32) | g;
     const TileRect rect = bin_rect(reference_rect(q0.x, q0.y, a.radii[g], a.gx, a.gy), a.bin_shift);
     SpanCtx s;
     if (!span_setup(s, q0.x, q0.y, q0.z, q0.w, q1.x, q1.z, rect, a.bin_shift)) continue;
@@ -448,8 +440,7 @@ void launch_bucket_scan(const BucketArgs& a, cudaStream_t st) {
 void launch_bucket_emit(const BucketArgs& a, cudaStream_t st) {
   if (a.P == 0 || a.capacity == 0) return;
   k_emit_bucket<<<(a.P + 255) / 256, 256, 0, st>>>(a);
-  k_emit_bucket_big<<<148 * 2, 256, 0, st>>>(a);
-  count_launch(2);
+  count_launch();
 }
 
 void launch_bucket_sort(const BucketArgs& a, cudaStream_t st) {
