@@ -69,3 +69,61 @@ def test_hinge_fixture_is_unit_axis():
     ax = np.array(GOLD["hinge"]["axis"])
     assert abs(np.linalg.norm(ax) - 1.0) < 1e-6
     assert GOLD["joint_limits"]["upper"] == 1.57
+
+
+# ---- Nerfstudio wire format (transforms.json / dataparser_transforms.json) vs the reference's readers ----------
+HERE = os.path.join(os.path.dirname(__file__), "golden")
+NS = json.load(open(os.path.join(HERE, "nerfstudio_golden.json")))
+
+
+def _uv_top_origin(cam, pts):
+    """Continuous image coordinates (u right, v DOWN from the top row, pixel k centred at k + 0.5) of world points
+    through the rasterizer's own projection matrix -- the convention of nerf2physic_utils.project_3d_to_2d."""
+    px, py = _pixel_centres(cam, np.asarray(pts))
+    return np.stack([px + 0.5, py + 0.5], 1)
+
+
+def test_parse_transforms_json_matches_reference_reader():
+    from robosimgs_b200.cameras import parse_transforms_json
+    fr = parse_transforms_json(os.path.join(HERE, "ns_transforms_global.json"))
+    K = np.array(NS["global"]["K"])
+    assert len(fr) == len(NS["global"]["c2w"]) == 5
+    for (c2w, fx, fy, cx, cy, w, h), ref_c2w, ref_w2c in zip(fr, NS["global"]["c2w"], NS["global"]["w2c"]):
+        assert np.array_equal(c2w, np.array(ref_c2w))
+        assert np.allclose(np.linalg.inv(c2w), np.array(ref_w2c), atol=1e-12)
+        assert (fx, fy, cx, cy) == (K[0, 0], K[1, 1], K[0, 2], K[1, 2]) and (w, h) == tuple(NS["image"])
+    frp = parse_transforms_json(os.path.join(HERE, "ns_transforms_perframe.json"))
+    for (c2w, fx, fy, cx, cy, w, h), Kp in zip(frp, NS["perframe"]["K"]):      # reference: different_Ks=True
+        Kp = np.array(Kp)
+        assert (fx, fy, cx, cy) == (Kp[0, 0], Kp[1, 1], Kp[0, 2], Kp[1, 2])
+
+
+def test_cameras_from_nerfstudio_project_like_the_reference():
+    """Cameras built from transforms.json project the reference's points where nerf2physic_utils.project_3d_to_2d puts
+    them (off-centre principal point, top-origin cy, global and per-frame intrinsics)."""
+    from robosimgs_b200.cameras import cameras_from_nerfstudio
+    pts = np.array(NS["points_orig"])
+    for key, fname in (("global", "ns_transforms_global.json"), ("perframe", "ns_transforms_perframe.json")):
+        cams = cameras_from_nerfstudio(os.path.join(HERE, fname))
+        for cam, uv in zip(cams, NS[key]["uv"]):
+            assert (cam.image_width, cam.image_height) == tuple(NS["image"])
+            assert np.abs(_uv_top_origin(cam, pts) - np.array(uv)).max() < 1e-3, key
+
+
+def test_dataparser_transform_matches_the_reference_convention():
+    """dataparser_transforms.json: the reference maps a Nerfstudio-space point back with inv([transform; 0 0 0 1/scale])
+    (load_ns_point_cloud); cameras moved INTO Nerfstudio space by cameras_from_nerfstudio(..., dataparser) must see the
+    Nerfstudio-space points exactly where the original cameras see the mapped-back points."""
+    from robosimgs_b200.cameras import apply_dataparser_transform, cameras_from_nerfstudio
+    dp = json.load(open(os.path.join(HERE, "ns_dataparser_transforms.json")))
+    assert np.array_equal(np.array(dp["transform"]), np.array(NS["dataparser"]["transform"])) and dp["scale"] == NS["dataparser"]["scale"]
+    cams = cameras_from_nerfstudio(os.path.join(HERE, "ns_transforms_global.json"), os.path.join(HERE, "ns_dataparser_transforms.json"))
+    pts_ns = np.array(NS["points_ns"])
+    for cam, uv in zip(cams, NS["global"]["uv"]):
+        assert np.abs(_uv_top_origin(cam, pts_ns) - np.array(uv)).max() < 1e-3
+    # the camera centre itself follows the same map: p_ns = scale * (R p + t)
+    c2w = np.array(NS["global"]["c2w"][0])
+    moved = apply_dataparser_transform(c2w, dp["transform"], dp["scale"])
+    T = np.array(dp["transform"])
+    assert np.allclose(moved[:3, 3], dp["scale"] * (T[:, :3] @ c2w[:3, 3] + T[:, 3]), atol=1e-12)
+    assert np.allclose(moved[:3, :3], T[:, :3] @ c2w[:3, :3], atol=1e-12)
