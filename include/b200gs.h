@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define B200GS_VERSION 101
+#define B200GS_VERSION 200
 
 /* Error codes (0 = success).  b200gs_last_error() returns the message for the calling thread. */
 #define B200GS_OK 0
@@ -214,6 +214,71 @@ typedef struct B200GSAdamGroup {
 } B200GSAdamGroup;
 int b200gs_adam_step(const B200GSAdamGroup* groups, int32_t num_groups, float beta1, float beta2, float eps,
                      int32_t step, void* stream);
+
+/*
+ * ---- Context: the no-stall protocol behind the C ABI ------------------------------------------------------------
+ * b200gs_forward leaves three things to its caller: scratch memory, the pair-capacity hint that lets a frame be
+ * launched before its pair count D is known, and the bin size that suits the scene's splat extent.  A context owns
+ * all three, so that a C / pybind caller gets the same behaviour as the Python operator layer with no state of its
+ * own (what the replaced interface's caller would otherwise have to rebuild around every rasterize_gaussians call):
+ *   - scratch arenas (stream-ordered device allocations, grown geometrically, reused from frame to frame);
+ *   - per (P, H, W): a slowly decaying maximum of recent pair counts -> hint = b200gs_policy_pair_capacity(D);
+ *   - per (P, H, W): the bin size, chosen on the first synchronous frame (and re-checked every 256th) from the
+ *     pairs-per-visible-Gaussian ratio and the frame's coverage -> b200gs_policy_bin_shift();
+ *   - a ring of pinned words + events for frames whose pair-count check is deferred (tickets).
+ * A context belongs to the device that was current at creation and serves ONE stream at a time (frames in flight on
+ * several streams: one context per stream); calls on one context are serialised by an internal mutex.
+ */
+typedef struct B200GSContext B200GSContext;
+int b200gs_context_create(B200GSContext** out_ctx);
+int b200gs_context_destroy(B200GSContext* ctx);
+
+/*
+ * Forward through a context.  Same tensors as b200gs_forward; prm->pair_capacity_hint and the bin-shift bits of
+ * prm->flags are ignored (the context supplies them).  An allocator whose `resize` is NULL selects the context's own
+ * arena for that buffer.
+ *   defer == 0: *num_rendered receives D (exact; the host waits for D only after the whole frame is queued, and only
+ *               redoes the binning stage if D exceeded the hint); *ticket = -1.
+ *   defer != 0: if a hint exists the call never waits: *ticket >= 0 identifies the frame, D arrives later --
+ *               b200gs_context_ticket_wait() tells whether the frame is complete (D <= hint); a frame that is not
+ *               must be rendered again with defer == 0.  Without a hint (first frame of a (P,H,W)) the call behaves
+ *               as defer == 0 and returns *ticket = -1.
+ * *used_flags receives the bin-shift bits the frame was rendered with: b200gs_context_backward (or b200gs_backward
+ * via prm->flags) must get them back.
+ */
+int b200gs_context_forward(B200GSContext* ctx, const B200GSParams* prm, const float* bg, const float* viewmatrix,
+                           const float* projmatrix, const float* campos, const float* means3D, const float* shs,
+                           const float* colors_precomp, const float* opacities, const float* scales,
+                           const float* rotations, const float* cov3D_precomp, float* out_color, int32_t* radii,
+                           B200GSAlloc geom, B200GSAlloc binning, B200GSAlloc img, int32_t defer,
+                           int32_t* num_rendered, int64_t* ticket, int32_t* used_flags, void* stream);
+
+/* Waits until the stream has passed the deferred frame `ticket`; *num_rendered = D, *complete = (D <= its hint). */
+int b200gs_context_ticket_wait(B200GSContext* ctx, int64_t ticket, int32_t* num_rendered, int32_t* complete);
+
+/* Backward for the LAST b200gs_context_forward of this context that used the context's own arenas (NULL geom /
+ * binning / img select them); otherwise identical to b200gs_backward.  used_flags: from that forward call. */
+int b200gs_context_backward(B200GSContext* ctx, const B200GSParams* prm, int32_t used_flags, const float* bg,
+                            const float* viewmatrix, const float* projmatrix, const float* campos,
+                            const float* means3D, const float* shs, const float* colors_precomp,
+                            const float* opacities, const float* scales, const float* rotations,
+                            const float* cov3D_precomp, const int32_t* radii, const char* geom, const char* binning,
+                            const char* img, int32_t num_rendered, const float* dL_dout_color, float* dL_dmeans3D,
+                            float* dL_dmeans2D, float* dL_dshs, float* dL_dcolors_precomp, float* dL_dopacities,
+                            float* dL_dscales, float* dL_drotations, float* dL_dcov3D, void* stream);
+
+/* What the context currently holds for (P, H, W): last tracked pair count (0 = none) and bin shift (-1 = automatic). */
+int b200gs_context_query(B200GSContext* ctx, int32_t P, int32_t image_height, int32_t image_width,
+                         int64_t* tracked_pairs, int32_t* bin_shift);
+
+/* The two rules of the protocol as pure host functions (no CUDA call; the Python operator layer uses the same):
+ *   pair capacity for a tracked pair count D:  D + D/16 + 32768   (0 for D <= 0);
+ *   bin shift for a frame that produced D pairs from `touching` visible Gaussians with (16 << used_shift)-px bins:
+ *   bins of about three splat extents, extent = (sqrt(D / touching) - 1) * bin edge, clamped to 32..256 px, and one
+ *   size coarser (256 px) when 128 px came out and the frame saturates everywhere (coverage > 0.995; pass a negative
+ *   coverage if unknown).  Returns used_shift unchanged when there is nothing to decide (D or touching <= 0). */
+int64_t b200gs_policy_pair_capacity(int64_t tracked_pairs);
+int32_t b200gs_policy_bin_shift(int64_t D, int64_t touching, int32_t used_shift, float coverage);
 
 /* Sizes of the forward scratch buffers for given P, H, W (geom, img) and D (binning); lets a
  * caller pre-size arenas.  Any of the out pointers may be NULL. */

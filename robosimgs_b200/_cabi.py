@@ -18,6 +18,8 @@ EXPORTED_SYMBOLS = (
     "b200gs_set_option", "b200gs_ply_activate", "b200gs_transform_gaussians",
     "b200gs_extract_alpha", "b200gs_photometric_loss", "b200gs_photometric_loss_backward",
     "b200gs_ssim_forward", "b200gs_ssim_backward", "b200gs_adam_step", "b200gs_geom_layout",
+    "b200gs_context_create", "b200gs_context_destroy", "b200gs_context_forward", "b200gs_context_ticket_wait",
+    "b200gs_context_backward", "b200gs_context_query", "b200gs_policy_pair_capacity", "b200gs_policy_bin_shift",
 )
 ADAM_MAX_GROUPS = 8
 DEFER_PAIR_CHECK = 1
@@ -108,6 +110,26 @@ def lib():
     L.b200gs_extract_alpha.argtypes = [vp, C.c_int32, C.c_int32, fp, vp]
     L.b200gs_geom_layout.restype = C.c_int
     L.b200gs_geom_layout.argtypes = [C.c_int32, C.POINTER(C.c_size_t)]
+    L.b200gs_policy_pair_capacity.restype = C.c_int64
+    L.b200gs_policy_pair_capacity.argtypes = [C.c_int64]
+    L.b200gs_policy_bin_shift.restype = C.c_int32
+    L.b200gs_policy_bin_shift.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_float]
+    L.b200gs_context_create.restype = C.c_int
+    L.b200gs_context_create.argtypes = [C.POINTER(C.c_void_p)]
+    L.b200gs_context_destroy.restype = C.c_int
+    L.b200gs_context_destroy.argtypes = [C.c_void_p]
+    L.b200gs_context_forward.restype = C.c_int
+    L.b200gs_context_forward.argtypes = [C.c_void_p, C.POINTER(B200GSParams), fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, fp,
+                                         fp, vp, B200GSAlloc, B200GSAlloc, B200GSAlloc, C.c_int32,
+                                         C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int32), vp]
+    L.b200gs_context_ticket_wait.restype = C.c_int
+    L.b200gs_context_ticket_wait.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.b200gs_context_backward.restype = C.c_int
+    L.b200gs_context_backward.argtypes = [C.c_void_p, C.POINTER(B200GSParams), C.c_int32, fp, fp, fp, fp, fp, fp, fp, fp,
+                                          fp, fp, fp, vp, vp, vp, vp, C.c_int32, fp, fp, fp, fp, fp, fp, fp, fp, fp, vp]
+    L.b200gs_context_query.restype = C.c_int
+    L.b200gs_context_query.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64),
+                                       C.POINTER(C.c_int32)]
     L.b200gs_set_option.restype = C.c_int
     L.b200gs_set_option.argtypes = [C.c_char_p, C.c_int]
     L.b200gs_profile_enable.argtypes = [C.c_int]

@@ -671,7 +671,8 @@ int b200gs_backward(const B200GSParams* prm, const float* bg, const float* viewm
 
   ProjectBwdArgs pa;
   pa.P = P; pa.M = prm->M; pa.W = W; pa.H = H;
-  pa.slab = getenv("B200GS_NO_SLAB") ? -1 : 0;
+  static const bool no_slab = getenv("B200GS_NO_SLAB") != nullptr;     // read once per process
+  pa.slab = no_slab ? -1 : 0;
   pa.sh_vec = (shs && (prm->M & 3) == 0 && (reinterpret_cast<uintptr_t>(shs) & 15) == 0 &&
                (reinterpret_cast<uintptr_t>(dL_dshs) & 15) == 0) ? 1 : 0;
   pa.tanfovx = prm->tanfovx; pa.tanfovy = prm->tanfovy; pa.scale_modifier = prm->scale_modifier;

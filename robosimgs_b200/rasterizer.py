@@ -95,7 +95,6 @@ class _ScratchPool:
 
 
 _POOL = _ScratchPool()
-LEASE_TAG = None
 
 
 class _Lease:
@@ -104,13 +103,13 @@ class _Lease:
     dict, not over the lease, so there is no reference cycle: dropping the last reference (e.g. the
     autograd node dying) returns the buffers to the pool immediately."""
 
-    def __init__(self, device, kinds):
+    def __init__(self, device, kinds, tag=None):
         self.device = device
         self.stream = torch.cuda.current_stream(device).cuda_stream
         self.tensors = tensors = {}
-        # LEASE_TAG (set by sweep.SceneRenderer) gives a caller private scratch: buffers used inside a
-        # captured CUDA graph must never be handed to eager calls on the same stream
-        keys = {k: (device.index, self.stream, k, LEASE_TAG) for k in kinds}
+        # tag (GaussianRasterizer.scratch_tag, set by sweep.SceneRenderer per frame slot) gives a caller private
+        # scratch: buffers used inside a captured CUDA graph must never be handed to eager calls on the same stream
+        keys = {k: (device.index, self.stream, k, tag) for k in kinds}
         self._keys = keys
 
         def make(kind):
@@ -145,7 +144,9 @@ class _Lease:
 # Pair-capacity hints (see B200GSParams.pair_capacity_hint): a slowly decaying maximum of the pair
 # counts of recent frames with the same (device, P, H, W), plus head-room -- so both a smooth camera
 # path and random training views stay under the hint.  Purely a performance hint: the library redoes
-# the binning stage exactly if a frame needs more.
+# the binning stage exactly if a frame needs more.  The two rules themselves (head-room, bin size from the
+# splat extent) live in the library -- b200gs_policy_pair_capacity / b200gs_policy_bin_shift, the same functions a
+# B200GSContext applies for C callers (include/b200gs.h) -- this layer only keeps the per-key state next to autograd.
 _PAIR_HINTS: dict = {}
 SPECULATE_PAIR_CAPACITY = True
 
@@ -186,18 +187,16 @@ def _adapt_bin_size(pol, used, hint_key, D, radii, coverage=None):
     pol["calls"] += 1
     if not ADAPT_BIN_SIZE or D <= 0 or not (pol["calls"] == 1 or pol["calls"] % 256 == 0):
         return
-    import math
     touch = int((radii > 0).sum())
     if touch <= 0:
         return
-    b = 16 << used
-    extent = max(math.sqrt(max(D / touch, 1.0)) - 1.0, 0.0) * b
-    new = min(4, max(1, int(round(math.log2(max(3.0 * extent, 16.0) / 16.0)))))
-    # large splats AND a frame that saturates everywhere: tiles stop after the first few records of their
-    # list, so one size coarser costs the compositing kernels nothing and makes emission and sort lighter
-    # (C3: 0.372 -> 0.356 ms); a frame that does not saturate walks its whole lists and must not go coarser
-    if new == 3 and coverage is not None and coverage() > 0.995:
-        new = 4
+    # bins of about three splat extents (32..256 px); one size coarser when 128 px came out and the frame saturates
+    # everywhere (C3: 0.372 -> 0.356 ms) -- the rule is b200gs_policy_bin_shift; the coverage (a device reduction)
+    # is only evaluated when it can matter
+    L = _cabi.lib()
+    new = int(L.b200gs_policy_bin_shift(int(D), touch, int(used), -1.0))
+    if new == 3 and coverage is not None:
+        new = int(L.b200gs_policy_bin_shift(int(D), touch, int(used), float(coverage())))
     if new != used:
         pol["shift"] = new
         _PAIR_HINTS.pop(hint_key, None)          # the pair count changes with the bin size
@@ -252,7 +251,8 @@ class DeferOptions(list):
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
-                cov3Ds_precomp, raster_settings, grad_mode=True, near_plane=0.0, want_alpha=False, ticket_box=None):
+                cov3Ds_precomp, raster_settings, grad_mode=True, near_plane=0.0, want_alpha=False, ticket_box=None,
+                scratch_tag=None):
         L = _cabi.lib()
         rs = raster_settings
         if getattr(rs, "antialiasing", False):
@@ -277,7 +277,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         H, W = int(rs.image_height), int(rs.image_width)
         hint_key = (dev.index, P, H, W)
         last_D = _PAIR_HINTS.get(hint_key, 0) if SPECULATE_PAIR_CAPACITY and not rs.debug else 0
-        hint = last_D + (last_D >> 4) + 32768 if last_D > 0 else 0
+        hint = int(L.b200gs_policy_pair_capacity(int(last_D)))
         # deferred pair check (forward-only callers that pass a ticket box): only once a hint exists
         ticket = None
         if ticket_box is not None:
@@ -296,7 +296,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         num_rendered = C.c_int32(0)
         nr_ptr = C.c_void_p(ticket.word.data_ptr()) if defer else C.cast(C.pointer(num_rendered), C.c_void_p)
         with torch.cuda.device(dev):
-            lease = _Lease(dev, ("geom", "binning", "img"))
+            lease = _Lease(dev, ("geom", "binning", "img"), scratch_tag)
             stream = C.c_void_p(lease.stream)
             _cabi.check(L.b200gs_forward(
                 C.byref(prm), _ptr(bg), _ptr(view), _ptr(proj), _ptr(campos), _ptr(means3D), _ptr(sh),
@@ -388,19 +388,21 @@ class _RasterizeGaussians(torch.autograd.Function):
         if g_sh is not None and sh_shape is not None:
             g_sh = g_sh.view(sh_shape)
         g_opac = g_opac.view(opac_shape)
-        return g_means3D, g_means2D, g_sh, g_col, g_opac, g_scales, g_rots, g_cov, None, None, None, None, None
+        return g_means3D, g_means2D, g_sh, g_col, g_opac, g_scales, g_rots, g_cov, None, None, None, None, None, None
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
-                        cov3Ds_precomp, raster_settings):
+                        cov3Ds_precomp, raster_settings, scratch_tag=None):
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
-                                     cov3Ds_precomp, raster_settings, torch.is_grad_enabled())
+                                     cov3Ds_precomp, raster_settings, torch.is_grad_enabled(), 0.0, False, None,
+                                     scratch_tag)
 
 
 class GaussianRasterizer(nn.Module):
     def __init__(self, raster_settings: GaussianRasterizationSettings):
         super().__init__()
         self.raster_settings = raster_settings
+        self.scratch_tag = None      # not None: this rasterizer leases PRIVATE scratch (see _Lease)
 
     def markVisible(self, positions: torch.Tensor) -> torch.Tensor:
         """Boolean mask of the Gaussians that pass the near-plane cull (view-space z > 0.2)."""
@@ -438,7 +440,7 @@ class GaussianRasterizer(nn.Module):
         with torch.no_grad():
             color, radii = _RasterizeGaussians.apply(
                 means3D.detach(), means2D.detach(), det(shs), det(colors_precomp), opacities.detach(), det(scales),
-                det(rotations), det(cov3D_precomp), self.raster_settings, False, 0.0, False, box)
+                det(rotations), det(cov3D_precomp), self.raster_settings, False, 0.0, False, box, self.scratch_tag)
         return color, radii, box[-1]
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None,
@@ -456,7 +458,7 @@ class GaussianRasterizer(nn.Module):
         rotations = empty if rotations is None else rotations
         cov3D_precomp = empty if cov3D_precomp is None else cov3D_precomp
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
-                                   cov3D_precomp, rs)
+                                   cov3D_precomp, rs, self.scratch_tag)
 
 
 def export_rgb8(color: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:

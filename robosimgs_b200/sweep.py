@@ -151,18 +151,15 @@ class SceneRenderer:
         sc = self.scene
         kw = dict(shs=sc["shs"], scales=sc["scales"], rotations=sc["rotations"])
         r = rz.GaussianRasterizer(rs)
+        r.scratch_tag = slot["tag"]       # private scratch per frame slot (captured graphs bake the pointers in)
         ticket = None
-        rz.LEASE_TAG = slot["tag"]
-        try:
-            if exact or self.capacity <= 0:
-                color, _ = r(sc["means3D"], self.means2D, sc["opacities"], **kw)
-            else:
-                opts = rz.DeferOptions(capacity=self.capacity, word=slot["word"], record_event=False)
-                color, _, ticket = r.forward_deferred(sc["means3D"], self.means2D, sc["opacities"], options=opts, **kw)
-            if self.host_frames:
-                rz.export_rgb8(color, out=slot["rgb8"])
-        finally:
-            rz.LEASE_TAG = None
+        if exact or self.capacity <= 0:
+            color, _ = r(sc["means3D"], self.means2D, sc["opacities"], **kw)
+        else:
+            opts = rz.DeferOptions(capacity=self.capacity, word=slot["word"], record_event=False)
+            color, _, ticket = r.forward_deferred(sc["means3D"], self.means2D, sc["opacities"], options=opts, **kw)
+        if self.host_frames:
+            rz.export_rgb8(color, out=slot["rgb8"])
         if self.host_frames:
             slot["frame_host"].copy_(slot["rgb8"], non_blocking=True)
         else:
