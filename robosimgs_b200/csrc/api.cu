@@ -144,6 +144,22 @@ static bool use_render4(int num_tiles16) {
   return m < 0 ? num_tiles16 >= RENDER4_MIN_TILES : m == 1;
 }
 
+// record slab: 1 = after the bucket sort the 48-byte records are copied into list order (k_build_slab) and the
+// four-pixel compositing kernels fill their shared-memory ring with ONE TMA bulk copy per 64-record chunk instead of
+// one LDGSTS gather per record; 0 (default) = gather from the per-Gaussian record table.  Needs the bucketed binning.
+// Process-wide: must not change between a forward call and its backward call.  b200gs_set_option("slab", 0|1),
+// B200GS_SLAB=1.  Measured A/B: DESIGN.md section 5.
+static std::atomic<int> g_slab_mode{-1};
+static bool use_slab() {
+  int m = g_slab_mode.load();
+  if (m < 0) {
+    const char* e = getenv("B200GS_SLAB");
+    m = (e && atoi(e) == 1) ? 1 : 0;
+    g_slab_mode.store(m);
+  }
+  return m == 1;
+}
+
 // pair keys of the global sort: 32-bit (bin << 24 | quantised depth, exact order restored in the ranges
 // pass; default whenever there are at most 255 bins and the library sort is used) or 64-bit.
 // b200gs_set_option("sort_keys", 32|64), B200GS_SORT_KEYS=64.
@@ -180,9 +196,12 @@ static GeomBuf carve_geom(char* base, int P, size_t* bytes) {
   return g;
 }
 
-static BinBuf carve_binning(char* base, int64_t D, int tile_bits, size_t* bytes) {
+static BinBuf carve_binning(char* base, int64_t D, int tile_bits, size_t* bytes, bool slab = false) {
   Carver c(base);
   BinBuf b;
+  // the FIRST chunk is what the backward pass reads, so its offset must not depend on the capacity: the record
+  // slab when there is one (it carries the Gaussian ids), else the sorted id list
+  b.slab = slab ? c.take<float4>((size_t)D * REC_F4) : nullptr;
   b.vals_sorted = c.take<uint32_t>(D);
   b.keys_sorted = c.take<uint64_t>(D);
   b.keys = c.take<uint64_t>(D);
@@ -304,6 +323,10 @@ int b200gs_set_option(const char* name, int value) {
   }
   if (name && !strcmp(name, "render")) {
     g_render_mode.store(value < 0 ? -1 : (value == 0 ? 0 : 1));
+    return 0;
+  }
+  if (name && !strcmp(name, "slab")) {
+    g_slab_mode.store(value == 1 ? 1 : 0);
     return 0;
   }
   if (name && !strcmp(name, "gather")) {
@@ -439,7 +462,7 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
   ba.total = gb.counters + 1; ba.big_queue = gb.big_queue; ba.big_count = gb.counters;
   ba.big_seg_count = gb.counters + 2; ba.total_windows = gb.counters + 3;
   ba.win_first = nullptr; ba.win_capacity = 0; ba.big_segs = nullptr;
-  ba.seg = nullptr; ba.seg_alt = nullptr; ba.vals_sorted = nullptr;
+  ba.seg = nullptr; ba.seg_alt = nullptr; ba.vals_sorted = nullptr; ba.slab = nullptr;
   const uint32_t* d_total = bucketed ? gb.counters + 1 : gb.offsets + (P > 0 ? P - 1 : 0);
   const int64_t hint_cap = (prm->pair_capacity_hint > 0 && prm->pair_capacity_hint < (int64_t)0x7fffffff)
                                ? prm->pair_capacity_hint : 0;
@@ -460,10 +483,11 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
   // ---- binning + compositing for a given pair capacity (D <= cap slots; [D,cap) are padding) ----
   auto run_binning_and_render = [&](uint32_t cap, const std::function<int()>* after_scan) -> int {
     size_t bin_bytes;
-    carve_binning(nullptr, cap, tile_bits, &bin_bytes);
+    const bool slab = bucketed && use_slab() && use_render4(gx * gy);
+    carve_binning(nullptr, cap, tile_bits, &bin_bytes, slab);
     char* bin_p = grow(binning, bin_bytes, "binning");
     if (!bin_p && bin_bytes) return B200GS_ERR_ALLOC;
-    BinBuf bb = carve_binning(bin_p, cap, tile_bits, nullptr);
+    BinBuf bb = carve_binning(bin_p, cap, tile_bits, nullptr, slab);
     int rc2;
     // global-sort pipeline: the ranges pass only writes bins that own pairs (the bucket scan writes every bin)
     if ((!bucketed || P == 0) &&
@@ -478,6 +502,7 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
         return rc2;
       BucketArgs b2 = ba;
       b2.capacity = cap; b2.seg = bb.keys; b2.seg_alt = bb.keys_sorted; b2.vals_sorted = bb.vals_sorted;
+      b2.slab = slab ? bb.slab : nullptr;
       b2.win_first = bb.win_first; b2.win_capacity = cap / BUCKET_WINDOW + BUCKET_BINS_MAX + 2; b2.big_segs = bb.big_segs;
       {
         StageTimer t(1, st);
@@ -555,7 +580,7 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
     }
     RenderArgs ra;
     ra.W = W; ra.H = H; ra.gbx = gbx; ra.bin_shift = bs; ra.ranges = ib.ranges; ra.point_list = bb.vals_sorted;
-    ra.rec = gb.rec; ra.bg = bg; ra.out_color = out_color;
+    ra.rec = gb.rec; ra.slab = (slab && cap > 0) ? bb.slab : nullptr; ra.bg = bg; ra.out_color = out_color;
     ra.pix = ib.pix; ra.n_contrib = ib.n_contrib;
     ra.vec4 = ((W & 3) == 0 && (reinterpret_cast<uintptr_t>(out_color) & 15) == 0) ? 1 : 0;
     {
@@ -646,7 +671,9 @@ int b200gs_backward(const B200GSParams* prm, const float* bg, const float* viewm
   const int gbx = (gx + (1 << bs) - 1) >> bs, gby = (gy + (1 << bs) - 1) >> bs;
   const int tile_bits = tile_bits_for(gbx * gby);
   GeomBuf gb = carve_geom(const_cast<char*>(geom), P, nullptr);
-  BinBuf bb = carve_binning(const_cast<char*>(binning), num_rendered, tile_bits, nullptr);
+  // the record slab exists iff the forward call ran the bucketed binning with option "slab" and the four-pixel kernels
+  const bool slab = use_slab() && use_render4(gx * gy) && use_bucketed() && (uint32_t)(gbx * gby) <= BUCKET_BINS_MAX;
+  BinBuf bb = carve_binning(const_cast<char*>(binning), num_rendered, tile_bits, nullptr, slab);
   ImgBuf ib = carve_img(const_cast<char*>(img), H, W, nullptr);
 
   const size_t g2_bytes = sizeof(float) * GRAD2D_STRIDE * (size_t)P;
@@ -658,7 +685,7 @@ int b200gs_backward(const B200GSParams* prm, const float* bg, const float* viewm
   if (num_rendered > 0) {
     RenderBwdArgs ra;
     ra.W = W; ra.H = H; ra.gbx = gbx; ra.bin_shift = bs; ra.ranges = ib.ranges; ra.point_list = bb.vals_sorted;
-    ra.rec = gb.rec; ra.bg = bg; ra.pix = ib.pix;
+    ra.rec = gb.rec; ra.slab = slab ? bb.slab : nullptr; ra.bg = bg; ra.pix = ib.pix;
     ra.n_contrib = ib.n_contrib; ra.dL_dpix = dL_dout_color; ra.grad2d = grad2d;
     ra.vec4 = ((W & 3) == 0 && (reinterpret_cast<uintptr_t>(dL_dout_color) & 15) == 0) ? 1 : 0;
     {

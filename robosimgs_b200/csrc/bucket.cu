@@ -304,6 +304,14 @@ __global__ void __launch_bounds__(32 * SORT_WARPS) k_bucket_sort(BucketArgs a) {
   else if (n <= 128) sort_bucket_in_registers<4>(seg, out, n, lane);
   else if (n <= 256) sort_bucket_in_registers<8>(seg, out, n, lane);
   else sort_bucket_in_registers<16>(seg, out, n, lane);
+  if (a.slab) {     // record slab for the TMA-fed compositing ring (option "slab"): slab[s + i] = rec[out[i]]
+    __syncwarp();   // the ids this warp just wrote are visible to all its lanes
+    float4* dst = a.slab + (size_t)s * REC_F4;
+    for (uint32_t q = lane; q < n * REC_F4; q += 32) {
+      const uint32_t i = q / REC_F4;
+      dst[q] = a.rec[(size_t)out[i] * REC_F4 + (q - i * REC_F4)];
+    }
+  }
 }
 
 // ---- k_bucket_sort_big (BinSortShared / bin_sort_pass: binsort.cuh) -----------------------------------
@@ -427,6 +435,13 @@ __global__ void __launch_bounds__(BS_THREADS) k_bucket_sort_big(BucketArgs a) {
     const uint64_t* F = (passes & 1) ? B : A;
     uint32_t* out = a.vals_sorted + s;
     for (uint32_t i = tid; i < n; i += BS_THREADS) out[i] = (uint32_t)__ldcg(F + i);
+    if (a.slab) {
+      float4* dst = a.slab + (size_t)s * REC_F4;
+      for (uint32_t q = tid; q < n * REC_F4; q += BS_THREADS) {
+        const uint32_t i = q / REC_F4;
+        dst[q] = a.rec[(size_t)(uint32_t)__ldcg(F + i) * REC_F4 + (q - i * REC_F4)];
+      }
+    }
     __syncthreads();
   }
 }

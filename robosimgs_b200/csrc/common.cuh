@@ -55,6 +55,7 @@ struct BinBuf {
   uint32_t* coop_hist;   // rotating digit histograms of the cooperative sort
   uint32_t* win_first;   // [D / BUCKET_WINDOW + BUCKET_BINS_MAX + 2] bucketed binning: first bucket of every sort window
   uint2* big_segs;       // [D / 512 + 2] bucketed binning: segments queued for the one-CTA sort
+  float4* slab;          // [D * 3] records in list order (option "gather" = 2), LAST chunk: absent otherwise
   char* cub_temp;
   size_t cub_temp_bytes;
 };

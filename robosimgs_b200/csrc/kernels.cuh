@@ -65,6 +65,7 @@ struct BucketArgs {
   uint32_t* big_seg_count;
   uint64_t *seg, *seg_alt;            // [capacity] ((depth bits - near bits) << 32 | id), ping-pong
   uint32_t* vals_sorted;              // [capacity] Gaussian ids in (bin, depth, index) order
+  float4* slab;                       // [capacity * 3] records in list order (option "slab") or nullptr
 };
 
 struct RangesArgs {
@@ -94,6 +95,7 @@ struct RenderArgs {
   const uint2* ranges;
   const uint32_t* point_list;  // Gaussian ids in (tile, depth) order
   const float4* rec;           // [P] projected-splat records
+  const float4* slab;          // [D] records in list order (written by the bucket sort) or nullptr: TMA-fed ring
   const float* bg;
   float* out_color;     // [3][H][W]
   float4* pix;          // [H*W]
@@ -106,6 +108,7 @@ struct RenderBwdArgs {
   const uint2* ranges;
   const uint32_t* point_list;
   const float4* rec;
+  const float4* slab;          // see RenderArgs
   const float* bg;
   const float4* pix;
   const uint32_t* n_contrib;
@@ -166,6 +169,7 @@ void launch_photometric_loss_bwd(const float* a, const float* b, size_t n, float
 void launch_bucket_scan(const BucketArgs& a, cudaStream_t st);
 void launch_bucket_emit(const BucketArgs& a, cudaStream_t st);
 void launch_bucket_sort(const BucketArgs& a, cudaStream_t st);
+
 
 // train.cu: fused SSIM and multi-tensor Adam
 void launch_ssim_fwd(const float* img1, const float* img2, int C, int H, int W, float* maps, float* out_sum,

@@ -60,15 +60,21 @@ __device__ __forceinline__ Tile4 tile4_setup(int W, int H, int warp, int lane) {
 #ifndef R4_BWD_MINB
 #define R4_BWD_MINB 12
 #endif
+template <bool SLAB>
 __global__ void __launch_bounds__(R4_THREADS, R4_FWD_MINB) k_render_fwd4(RenderArgs a) {
   __shared__ __align__(128) float4 sm[R4_STAGES][R4_CH * REC_F4];
+  __shared__ __align__(8) uint64_t s_bar[R4_STAGES];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint2 range = a.ranges[(blockIdx.y >> a.bin_shift) * a.gbx + (blockIdx.x >> a.bin_shift)];
   const bool coarse = a.bin_shift != 0;
   const uint32_t n = range.y - range.x;
   const uint32_t nchunks = (n + R4_CH - 1) / R4_CH;
-  Ring4 ring{sm, a.point_list + range.x, a.rec, n, nchunks, 0u, tid};
+  using Ring = std::conditional_t<SLAB, Ring4Slab, Ring4>;
+  Ring ring = [&]() {
+    if constexpr (SLAB) return Ring4Slab{sm, s_bar, a.slab + (size_t)range.x * REC_F4, n, nchunks, tid};
+    else return Ring4{sm, a.point_list + range.x, a.rec, n, nchunks, 0u, tid};
+  }();
   const Tile4 t = tile4_setup(a.W, a.H, warp, lane);
 
   ring.prologue();
@@ -140,8 +146,10 @@ __global__ void __launch_bounds__(R4_THREADS, R4_FWD_MINB) k_render_fwd4(RenderA
   };
   auto all_done = [&]() { return fmaxf(fmaxf(T[0].x, T[0].y), fmaxf(T[1].x, T[1].y)) < 0.f; };
 
-  for (uint32_t c = 0; c < nchunks; c++) {
-    ring.wait();
+  uint32_t c = 0;
+  bool early = false;
+  for (; c < nchunks; c++) {
+    ring.wait(c);
     const uint32_t cnt = ring.count(c);
     const float4* st = sm[c % R4_STAGES];
     for (uint32_t base = 0; base < cnt; base += 32) {
@@ -167,10 +175,16 @@ __global__ void __launch_bounds__(R4_THREADS, R4_FWD_MINB) k_render_fwd4(RenderA
       }
     }
     const int num_done = __syncthreads_count(all_done());
-    if (num_done == R4_THREADS) break;
+    if (num_done == R4_THREADS) { early = true; break; }
     ring.refill(c);
   }
-  r4_cp_async_wait<0>();   // no asynchronous copy may still target this CTA's shared memory
+  // no asynchronous copy may still target this CTA's shared memory when it exits: LDGSTS groups are drained; bulk
+  // copies that were issued ahead of a tile that finished early are waited for by the thread that issued them
+  if constexpr (SLAB) {
+    if (early && tid == 0)
+      for (uint32_t k = c + 1; k < min(nchunks, c + R4_STAGES); k++) ring.wait(k);
+  }
+  ring.drain();
 
   const float Tf[4] = {fabsf(T[0].x), fabsf(T[0].y), fabsf(T[1].x), fabsf(T[1].y)};
   const float R_[4] = {Cr[0].x, Cr[0].y, Cr[1].x, Cr[1].y};
@@ -239,15 +253,21 @@ __device__ __forceinline__ void r4_warp_reduce9(float (&v)[8], float& v8, int la
 //   dL/dalpha_j = T_j <c_j, g> - (F - R_j) / (1 - alpha_j),  F = <C_final, g> + T_final <bg, g>,
 //   R_j = sum_{k<=j} w_k <c_k, g>.
 // ==================================================================================================
+template <bool SLAB>
 __global__ void __launch_bounds__(R4_THREADS, R4_BWD_MINB) k_render_bwd4(RenderBwdArgs a) {
   __shared__ __align__(128) float4 sm[R4_STAGES][R4_CH * REC_F4];
+  __shared__ __align__(8) uint64_t s_bar[R4_STAGES];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint2 range = a.ranges[(blockIdx.y >> a.bin_shift) * a.gbx + (blockIdx.x >> a.bin_shift)];
   const bool coarse = a.bin_shift != 0;
   const uint32_t n = range.y - range.x;
   const uint32_t nchunks = (n + R4_CH - 1) / R4_CH;
-  Ring4 ring{sm, a.point_list + range.x, a.rec, n, nchunks, 0u, tid};
+  using Ring = std::conditional_t<SLAB, Ring4Slab, Ring4>;
+  Ring ring = [&]() {
+    if constexpr (SLAB) return Ring4Slab{sm, s_bar, a.slab + (size_t)range.x * REC_F4, n, nchunks, tid};
+    else return Ring4{sm, a.point_list + range.x, a.rec, n, nchunks, 0u, tid};
+  }();
   const Tile4 t = tile4_setup(a.W, a.H, warp, lane);
 
   ring.prologue();
@@ -301,8 +321,10 @@ __global__ void __launch_bounds__(R4_THREADS, R4_BWD_MINB) k_render_bwd4(RenderB
   }
   const uint32_t ncmax = max(max(nc[0], nc[1]), max(nc[2], nc[3]));
 
-  for (uint32_t c = 0; c < nchunks; c++) {
-    ring.wait();
+  uint32_t c = 0;
+  bool early = false;
+  for (; c < nchunks; c++) {
+    ring.wait(c);
     const uint32_t cnt = ring.count(c);
     const float4* st = sm[c % R4_STAGES];
     for (uint32_t base = 0; base < cnt; base += 32) {
@@ -387,21 +409,27 @@ __global__ void __launch_bounds__(R4_THREADS, R4_BWD_MINB) k_render_bwd4(RenderB
       }
     }
     const int num_done = __syncthreads_count(c * R4_CH + cnt >= ncmax);
-    if (num_done == R4_THREADS) break;
+    if (num_done == R4_THREADS) { early = true; break; }
     ring.refill(c);
   }
-  r4_cp_async_wait<0>();
+  if constexpr (SLAB) {
+    if (early && tid == 0)
+      for (uint32_t k = c + 1; k < min(nchunks, c + R4_STAGES); k++) ring.wait(k);
+  }
+  ring.drain();
 }
 
 void launch_render4(const RenderArgs& a, cudaStream_t st) {
   const dim3 grid((a.W + TILE - 1) / TILE, (a.H + TILE - 1) / TILE), block(R4_THREADS);
-  k_render_fwd4<<<grid, block, 0, st>>>(a);
+  if (a.slab) k_render_fwd4<true><<<grid, block, 0, st>>>(a);
+  else k_render_fwd4<false><<<grid, block, 0, st>>>(a);
   count_launch();
 }
 
 void launch_render_bwd4(const RenderBwdArgs& a, cudaStream_t st) {
   const dim3 grid((a.W + TILE - 1) / TILE, (a.H + TILE - 1) / TILE), block(R4_THREADS);
-  k_render_bwd4<<<grid, block, 0, st>>>(a);
+  if (a.slab) k_render_bwd4<true><<<grid, block, 0, st>>>(a);
+  else k_render_bwd4<false><<<grid, block, 0, st>>>(a);
   count_launch();
 }
 

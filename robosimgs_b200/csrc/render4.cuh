@@ -85,15 +85,51 @@ struct Ring4 {
     for (int s = 0; s < R4_STAGES; s++) issue(s, ids[s]);
     next_id = load_id(R4_STAGES);
   }
-  __device__ __forceinline__ void wait() {
+  __device__ __forceinline__ void wait(uint32_t) {
     r4_cp_async_wait<R4_STAGES - 1>();
     __syncthreads();
   }
+  __device__ __forceinline__ void drain() { r4_cp_async_wait<0>(); }   // no copy may still target this CTA's smem
   // stage c % R4_STAGES is free (caller synchronised the CTA): refill it with chunk c + R4_STAGES
   __device__ __forceinline__ void refill(uint32_t c) {
     issue(c + R4_STAGES, next_id);
     next_id = load_id(c + R4_STAGES + 1);
   }
+};
+
+// Same ring fed by TMA from the bin-ordered record SLAB (the bucket sort writes rec[point_list[i]] to slab[i], so a
+// tile's list is one contiguous run of 48-byte records): thread 0 arms the stage's mbarrier with the
+// chunk's byte count and issues ONE cp.async.bulk of up to 64 records (3 KB); everybody waits on the barrier's phase.
+struct Ring4Slab {
+  float4 (*sm)[R4_CH * REC_F4];
+  uint64_t* bar;            // [R4_STAGES] in shared memory
+  const float4* slab;       // first record of this tile's list
+  uint32_t n, nchunks;
+  int tid;
+
+  __device__ __forceinline__ uint32_t count(uint32_t c) const { return min((uint32_t)R4_CH, n - c * R4_CH); }
+  __device__ __forceinline__ void issue(uint32_t c) {
+    if (tid == 0 && c < nchunks) {
+      const uint32_t bytes = count(c) * (uint32_t)(REC_F4 * sizeof(float4));
+      mbar_expect_tx(&bar[c % R4_STAGES], bytes);
+      tma_load_1d(&sm[c % R4_STAGES][0], slab + (size_t)c * R4_CH * REC_F4, bytes, &bar[c % R4_STAGES]);
+    }
+  }
+  __device__ __forceinline__ void prologue() {
+    if (tid == 0) {
+#pragma unroll
+      for (int s = 0; s < R4_STAGES; s++) mbar_init(&bar[s], 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < R4_STAGES; s++) issue(s);
+  }
+  // chunk c is the (c / R4_STAGES)-th use of its stage: phase parity alternates per use
+  __device__ __forceinline__ void wait(uint32_t c) { mbar_wait(&bar[c % R4_STAGES], (c / R4_STAGES) & 1u); }
+  // stage c % R4_STAGES is free (caller synchronised the CTA): refill it with chunk c + R4_STAGES
+  __device__ __forceinline__ void refill(uint32_t c) { issue(c + R4_STAGES); }
+  __device__ __forceinline__ void drain() {}
 };
 
 // Per-record terms shared by the four pixels of a thread (a row): with the conic scaled by

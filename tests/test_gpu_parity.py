@@ -560,3 +560,33 @@ def test_bucket_sort_size_classes_match_the_global_sort(P, spread):
         _cabi.set_option("bin_shift", -1)
         _cabi.set_option("sort", 1)
         _cabi.set_option("sort_keys", 32)
+
+
+def test_record_slab_tma_ring_is_bit_identical():
+    """Option "slab": the four-pixel compositing kernels fill their ring with TMA bulk copies from the bin-ordered record
+    slab (k_build_slab) instead of per-record LDGSTS gathers -- images, radii and gradients must not change; long lists
+    (many chunks per tile, early exits with copies in flight) and tiny ones."""
+    from oracle import gs_oracle
+    from robosimgs_b200 import _cabi
+    sc, cam, rs = small_scene(P=6000, degree=1, W=320, H=208, opacity_boost=2.0)
+    sc.scales[:300] *= 6
+    w = torch.rand(3, 208, 320, generator=torch.Generator().manual_seed(31))
+    res = {}
+    try:
+        _cabi.set_option("render", 1)
+        for slab in (0, 1):
+            _cabi.set_option("slab", slab)
+            for shift in (0, 2):
+                _cabi.set_option("bin_shift", shift)
+                res[(slab, shift)] = gpu_render(sc, cam, 1, bg=(0.2, 0.1, 0.4), grad_weight=w)
+        base = res[(0, 0)]
+        for key, (color, radii, grads) in res.items():
+            assert np.array_equal(color, base[0]) and np.array_equal(radii, base[1]), key
+            for k in grads:
+                assert max_rel_err(grads[k], base[2][k]) < 1e-5, (key, k)
+        ref = gs_oracle.backward(_oracle(rs, sc), w.numpy())
+        _check_grads(res[(1, 2)][2], ref, ("means3D", "shs", "opacities", "scales", "rotations", "means2D"))
+    finally:
+        _cabi.set_option("slab", 0)
+        _cabi.set_option("bin_shift", -1)
+        _cabi.set_option("render", -1)

@@ -1,6 +1,6 @@
 """A/B of library builds on one GPU box (dev tool): for each libb200gs build given on the command line, the C3 sweep
 rate (SceneRenderer, 4 streams, graphs), the single-stream frame time with per-stage times, and the train step.
-usage: python tools/ab_quick.py tag=path/to/lib.so [tag=path ...]   (runs each in a fresh process)"""
+usage: python tools/ab_quick.py tag=path/to/lib.so[,ENV=VALUE...] [tag=...]   (runs each in a fresh process)"""
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -61,8 +61,10 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     sys.exit(0)
 
 for spec in sys.argv[1:]:
-    tag, path = spec.split("=", 1)
+    tag, rest = spec.split("=", 1)
+    path, *envs = rest.split(",")
     env = dict(os.environ, B200GS_LIB_PATH=os.path.abspath(path))
+    env.update(dict(e.split("=", 1) for e in envs))
     out = subprocess.run([sys.executable, __file__, "--child"], env=env, capture_output=True, text=True)
     line = out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-400:]
     print(tag, line, flush=True)
