@@ -421,7 +421,7 @@ def run_b200(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "P": P_SCENE, "P_vis": P_vis, "D_pairs": D, "sh_degree": SH_DEG,
-                   "image": [W_IMG, H_IMG], "tile": 16, "parallelism": f"camera-sharded x{world}, scene replicated",
+                   "image": [W_IMG, H_IMG], "tile": 16, "parallelism": f"camera-sharded x{world}, scene replicated", "binning": "depth-sliced buckets (bucket.cu), no library scan/sort",
                    "streams": f"{args.streams} CUDA streams per GPU, consecutive frames alternate (independent frames "
                               "overlap), one captured CUDA graph per frame slot, pair-count check deferred (every frame "
                               "validated inside the timed region), cameras and frames resident in HBM; "

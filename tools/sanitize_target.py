@@ -1,7 +1,7 @@
 """Small fwd+bwd cases for compute-sanitizer (memcheck / racecheck / synccheck): both compositing kernel
-families, both record-gather modes, both binning pipelines, library sort with 32- and 64-bit keys (tie
-repair incl. long runs), cooperative sort, bin shifts auto/0/2, long lists crossing ring stages, ragged image,
-fused SSIM / Adam / photometric loss."""
+families, both record-gather modes and the TMA-fed slab ring, both binning pipelines (depth-sliced buckets: warp sort,
+one-CTA radix for fat segments; library sort with 32- and 64-bit keys, tie repair incl. long runs; cooperative sort),
+bin shifts auto/0/2, long lists crossing ring stages, ragged image, fused SSIM / Adam / photometric loss."""
 import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -11,11 +11,12 @@ from robosimgs_b200 import _cabi
 from robosimgs_b200.scenes import Scene
 quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
 cases = ((3000, 200, 136, 3, -1), (6000, 64, 48, 0, 0), (500, 37, 23, 1, 2))
-modes = [dict(render=1, gather=1, binning=0, sort=1, sort_keys=32), dict(render=0, gather=1, binning=0, sort=0, sort_keys=32),
-         dict(render=0, gather=0, binning=0, sort=2, sort_keys=64), dict(render=1, gather=1, binning=1, sort=1, sort_keys=32),
-         dict(render=1, gather=1, binning=0, sort=0, sort_keys=64)]
+modes = [dict(render=1, gather=1, binning=0, sort=1, sort_keys=32, slab=0), dict(render=0, gather=1, binning=0, sort=0, sort_keys=32, slab=0),
+         dict(render=0, gather=0, binning=0, sort=2, sort_keys=64, slab=0), dict(render=1, gather=1, binning=1, sort=1, sort_keys=32, slab=0),
+         dict(render=1, gather=1, binning=0, sort=0, sort_keys=64, slab=0), dict(render=1, gather=1, binning=1, sort=1, sort_keys=32, slab=1),
+         dict(render=0, gather=1, binning=1, sort=1, sort_keys=32, slab=0)]
 if quick:
-    modes, cases = modes[:2] + modes[3:4], cases[:2]
+    modes, cases = [modes[0], modes[3], modes[5]], cases[:2]
 for m in modes:
     for k, v in m.items():
         _cabi.set_option(k, v)
@@ -33,7 +34,17 @@ for m in modes:
     _cabi.set_option("bin_shift", -1)
     color, _, _ = gpu_render(flat, cam, 0, bg=(0.2, 0.1, 0.4), grad_weight=torch.rand(3, 64, 96))
     print("ok ties", m, float(color.mean()), flush=True)
-for k, v in dict(render=-1, gather=1, binning=-1, sort=1, sort_keys=32, bin_shift=-1).items():
+    # a wall facing the camera: fat buckets -> the one-CTA radix path of the bucket sort
+    if m["binning"] == 1:
+        g = torch.Generator().manual_seed(3)
+        P = 9000
+        wall = Scene(torch.cat([torch.rand(P, 2, generator=g) * 2 - 1, torch.zeros(P, 1)], 1), sc.shs[:1].repeat(P, 1, 1),
+                     torch.rand(P, 1, generator=g) * 0.3 + 0.05, torch.rand(P, 3, generator=g) * 0.03 + 0.01,
+                     torch.tensor([[1.0, 0, 0, 0]]).repeat(P, 1), 0)
+        _cabi.set_option("bin_shift", 3)
+        color, _, _ = gpu_render(wall, cam, 0, bg=(0.2, 0.1, 0.4), grad_weight=torch.rand(3, 64, 96))
+        print("ok wall", m, float(color.mean()), flush=True)
+for k, v in dict(render=-1, gather=1, binning=-1, sort=1, sort_keys=32, bin_shift=-1, slab=0).items():
     _cabi.set_option(k, v)
 from robosimgs_b200.losses import gs_loss
 from robosimgs_b200.optim import FusedAdam
