@@ -183,6 +183,8 @@ def run_b200(args):
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback in the product path)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from robosimgs_b200.sweep import bind_rank_to_cores
+    cores = bind_rank_to_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))     # before any pinned allocation
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -373,6 +375,17 @@ def run_b200(args):
     checksum = float(last_frame[0].double().mean())
     e2e_redone = [renderer.redone]
 
+    # ---- host ceiling of the e2e path: every rank copies finished frames device -> pinned host memory back to back,
+    # all ranks at once, nothing else running (what the box can absorb; the e2e sweep cannot beat it) ----
+    d2h_src = torch.empty(d2h_bytes, dtype=torch.uint8, device=dev)
+    d2h_dst = [torch.empty(d2h_bytes, dtype=torch.uint8).pin_memory() for _ in range(4)]
+    def d2h_step(s_):
+        d2h_dst[s_ % 4].copy_(d2h_src, non_blocking=True)
+    timed(d2h_step, 50)
+    d2h_ms = timed(d2h_step, 400)
+    d2h_gbs = world * 400 * d2h_bytes / (d2h_ms * 1e-3) / 1e9
+    del d2h_src, d2h_dst
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -441,6 +454,12 @@ def run_b200(args):
                 "ms_per_step_runs": [round(t / K, 5) for t in e2e_runs],
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "frames_rendered_twice": e2e_redone[0], "streams": NS,
+                "GBps_to_host": round(world * K * d2h_bytes / (e2e_ms * 1e-3) / 1e9, 2),
+                "host_d2h_ceiling_GBps": round(d2h_gbs, 2),
+                "frac_of_host_ceiling": round((world * K * d2h_bytes / (e2e_ms * 1e-3) / 1e9) / d2h_gbs, 3),
+                "host_binding": (f"rank bound to {len(cores)} host cores before pinned allocation" if cores else "none"),
+                "host_ceiling_what": "all ranks copying 6.2 MB frames device -> pinned host memory back to back, nothing else "
+                                     "running (max over ranks, same timing harness): the rate this box absorbs",
                 "cuda_graphs": not args.no_graphs,
                 "what": "robosimgs_b200.sweep.SceneRenderer.submit/collect per frame: camera (view, proj, campos) from "
                         "pinned host memory, forward with deferred pair check + export_rgb8, finished 8-bit RGB frame "

@@ -64,6 +64,25 @@ def default_render_fn(scene: dict, sh_degree: int, bg: torch.Tensor, deferred: b
     return render
 
 
+def bind_rank_to_cores(local_rank: int, local_world: int):
+    """Give each rank of a single-node job its own slice of the host cores BEFORE it allocates pinned memory (first
+    touch places the pages next to those cores).  With eight ranks copying 8-bit 1080p frames to host memory at once the
+    box's aggregate device->host rate rose from 123 to 159 GB/s (tools/d2h_ceiling.py, profiles/r2_d2h_ceiling_n8.json)
+    although nvidia-smi reports a single NUMA node.  Returns the cores kept (None if the platform has no affinity API)."""
+    if local_world <= 1 or not hasattr(os, "sched_getaffinity"):
+        return None
+    cpus = sorted(os.sched_getaffinity(0))
+    per = len(cpus) // local_world
+    if per < 1:
+        return None
+    mine = cpus[local_rank * per:(local_rank + 1) * per]
+    try:
+        os.sched_setaffinity(0, set(mine))
+    except OSError:
+        return None
+    return mine
+
+
 class FrameStreams:
     """Round-robin CUDA streams for INDEPENDENT frames of a sweep.
 
@@ -171,7 +190,9 @@ class SceneRenderer:
             self.capacity = 0
             return
         q = 1 << 16
-        need = ((int(pairs * 1.0625) + 32768 + q - 1) // q) * q
+        # head-room: 6 % on a tracked count, 25 % after an overflow (a camera path that keeps growing the pair count
+        # would otherwise re-capture every slot's graph again and again)
+        need = ((int(pairs * (1.25 if grow_only else 1.0625)) + 32768 + q - 1) // q) * q
         # grow_only: a frame that overflowed may have been submitted under an OLDER, smaller capacity than the
         # current one (several frames are in flight); its pair count must never shrink the capacity again
         self.capacity = max(self.capacity, need) if grow_only else need
@@ -224,6 +245,10 @@ class SceneRenderer:
             # pair capacity exceeded (abrupt view change): render this frame again, exactly; later
             # frames use (and graphs are re-captured for) the larger capacity
             self.redone += 1
+            if os.environ.get("B200GS_DEBUG_SWEEP"):
+                import sys
+                print(f"[sweep] frame {handle}: pairs {t.pairs} > capacity {t.hint} (current {self.capacity}): re-render",
+                      file=sys.stderr, flush=True)
             self._set_capacity(t.pairs, grow_only=True)
             with torch.no_grad(), torch.cuda.stream(slot["stream"]):
                 self._enqueue(slot, float(slot["cam"].tanfovx), float(slot["cam"].tanfovy), exact=True, in_capture=False)
@@ -317,6 +342,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    bind_rank_to_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -337,8 +363,13 @@ def main():
             acc += float(r.collect(pend.pop(0))[::64, ::64].float().mean())
         return acc
 
-    run(2)                                   # warm-up: exact first frame, graph capture per slot
+    for _ in range(6):                       # warm-up: exact first frame, graph capture per slot -- until a whole
+        before = r.redone                    # pass needed no re-render (the pair capacity has seen every camera)
+        run(1)
+        if r.redone == before and _ > 0:
+            break
     torch.cuda.synchronize()
+    r.redone = 0
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
