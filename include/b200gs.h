@@ -318,11 +318,16 @@ int64_t b200gs_launch_count(int reset);
  *   "render":     -1 automatic (default: four pixels per thread from 4096 tiles up, one pixel per thread
  *                 below), 1 compositing kernels with four pixels per thread, 0 one pixel per thread
  *   "gather":     1 LDGSTS record gather in the one-pixel compositing kernels (default), 0 TMA bulk copies
+ *   "slab":       0 (default) the four-pixel compositing kernels gather records with LDGSTS; 1 the bucket sort also
+ *                 writes the records in list order and the ring is filled by one TMA bulk copy per 64-record chunk
+ *                 (must not change between a forward call and its backward call)
+ *   "project":    0 (default) projection kernel with one thread per Gaussian; 1 dense-warp variant (warp-level
+ *                 stream compaction: cull -> geometry -> colour)
  *   "sort":       0 CUB radix sort, 1 automatic (default: single-launch cooperative radix sort for
  *                 pair lists <= 256 k, CUB above), 2 cooperative sort whenever the list is <= 3 M
  * Environment equivalents read at first use: B200GS_BIN_SHIFT, B200GS_GATHER=tma|ldgsts,
  * B200GS_SORT=cub|auto|coop,
- * B200GS_RENDER=auto|4px|1px, B200GS_BINNING=bucket|sort, B200GS_SORT_KEYS=64.
+ * B200GS_RENDER=auto|4px|1px, B200GS_BINNING=bucket|sort, B200GS_SORT_KEYS=64, B200GS_SLAB=1, B200GS_PROJECT=compact.
  */
 int b200gs_set_option(const char* name, int value);
 

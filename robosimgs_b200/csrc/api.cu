@@ -325,6 +325,10 @@ int b200gs_set_option(const char* name, int value) {
     g_render_mode.store(value < 0 ? -1 : (value == 0 ? 0 : 1));
     return 0;
   }
+  if (name && !strcmp(name, "project")) {
+    set_project_mode(value);
+    return 0;
+  }
   if (name && !strcmp(name, "slab")) {
     g_slab_mode.store(value == 1 ? 1 : 0);
     return 0;

@@ -15,7 +15,9 @@ constexpr int GRAD2D_STRIDE = 12;   // floats per Gaussian in the screen-space g
 // ---- projected-splat record (48 B, three float4) ----------------------------------------------
 //   q0 = { x, y, A, B }            pixel centre, conic
 //   q1 = { C, opacity, thr, idx }  thr = ln(255*opacity) + slack: 0.5*q <= thr  <=>  alpha >= 1/255
-//   q2 = { r, g, b, depth }
+//   q2 = { r, g, b, +-radius }     radius as a float; NEGATIVE marks a record that needs the general evaluation in
+//                                  the compositing kernels (opacity > 0.99: the min(0.99, .) clamp can bind; or a
+//                                  conic that is not safely positive definite: `power` may round above 0)
 // One record per Gaussian (geom buffer, 16-byte aligned): the unit a single 48-byte TMA bulk copy
 // gathers into a compositing CTA's shared-memory ring.
 

@@ -140,6 +140,7 @@ void launch_extract_alpha(const float4* pix, size_t npx, float* out, cudaStream_
 void launch_project_bwd(const ProjectBwdArgs& a, int deg, cudaStream_t st);
 void launch_render(const RenderArgs& a, cudaStream_t st);
 void launch_render_bwd(const RenderBwdArgs& a, cudaStream_t st);
+void set_project_mode(int mode);   // 0: one thread per Gaussian (default), 1: dense-warp projection kernel
 void set_gather_mode(int mode);  // 0: TMA bulk copy per record, 1: LDGSTS
 // render4.cu: four pixels per thread (default); render.cu keeps the one-pixel-per-thread kernels
 void launch_render4(const RenderArgs& a, cudaStream_t st);

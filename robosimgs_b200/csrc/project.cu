@@ -5,6 +5,9 @@
 // a11 preprocessCUDA bwd, a12 checkFrustum -- of the public diff-gaussian-rasterization named by
 // BASELINE.json:north_star (third-party; the reference repo only delegates, README.md:75).
 // Arithmetic follows oracle/gs_oracle_impl.h step by step.
+#include <atomic>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "spans.cuh"
@@ -97,6 +100,15 @@ __device__ __forceinline__ void cov2d(const Ewa& e, const float* c3, float& a, f
   a = ms[0][0] * e.m[0][0] + ms[0][1] * e.m[0][1] + ms[0][2] * e.m[0][2] + 0.3f;
   b = ms[0][0] * e.m[1][0] + ms[0][1] * e.m[1][1] + ms[0][2] * e.m[1][2];
   c = ms[1][0] * e.m[1][0] + ms[1][1] * e.m[1][1] + ms[1][2] * e.m[1][2] + 0.3f;
+}
+
+// Records whose alpha needs the general evaluation (see common.cuh, q2.w): opacity above the 0.99 clamp, or a conic
+// whose quadratic form is not positive by a margin that dwarfs fp32 rounding (then `power` > 0 can occur and such
+// pixels are skipped, as in the public algorithm).  For all others alpha = o * 2^power2 <= o <= 0.99 and power <= 0
+// hold for every pixel, so the compositing kernels can drop both tests without changing a bit.
+__device__ __forceinline__ bool record_is_general(float A, float B, float C, float o) {
+  const bool safe = A > 0.f && C > 0.f && (A * C - B * B) > 1e-4f * (A * C);
+  return o > 0.99f || !safe;
 }
 
 #define SH_C0 0.28209479177387814f
@@ -244,7 +256,7 @@ __global__ void __launch_bounds__(256, PROJECT_MIN_BLOCKS) k_project(ProjectArgs
           float4* rec = a.rec + (size_t)i * REC_F4;
           rec[0] = make_float4(px, py, A, B);
           rec[1] = make_float4(C, o, thr, __uint_as_float((uint32_t)i));
-          rec[2] = make_float4(rgb[0], rgb[1], rgb[2], (float)irad);
+          rec[2] = make_float4(rgb[0], rgb[1], rgb[2], record_is_general(A, B, C, o) ? -(float)irad : (float)irad);
         }
       }
     }
@@ -252,6 +264,164 @@ __global__ void __launch_bounds__(256, PROJECT_MIN_BLOCKS) k_project(ProjectArgs
   a.radii[i] = radius;
   a.depth_key[i] = key;
   a.tiles[i] = ntiles;
+}
+
+// ==================================================================================================
+// K1 with DENSE WARPS.  Only a third of a scene's Gaussians survive the cull, scattered at random over the index
+// space, so in k_project above every warp walks the whole visible path with a third of its lanes (ncu: 28.6 M
+// warp-instructions on C3, long-scoreboard bound: the 12 SH loads of a lane are issued behind three dependent round
+// trips).  Here a warp owns PC_CHUNK = 128 consecutive Gaussians and works in three stages with a warp-private queue
+// in shared memory between them (ballot + popc compaction, __syncwarp only, no block barrier):
+//   1. cull: view depth of 4 Gaussians per lane (12 independent loads), defaults for the culled ones;
+//   2. geometry for the survivors, 32 at a time: conic, radius, rect, tight spans, bucket counters, record q0/q1;
+//   3. colour for those that touch a bin, 32 at a time: the 12 x 128-bit SH loads of all 32 lanes in flight at once.
+// Same arithmetic per Gaussian as k_project, bit for bit (option "project": 1 = this kernel, 0 = k_project, default).
+// Measured on C3 (B200, ncu): 24.3 M instead of 28.6 M warp-instructions -- the near-plane cull only removes 45 % of
+// the Gaussians and the geometry stage (spans, sqrt/rcp) dominates -- at 34 % instead of 43 % occupancy (72 registers,
+// two queues): 0.061-0.070 ms against 0.061 ms.  Kept as the second implementation the parity tests cross-check.
+// ==================================================================================================
+constexpr int PC_CHUNK = 128;
+constexpr int PC_WARPS = 4;
+
+template <int DEG>
+__global__ void __launch_bounds__(32 * PC_WARPS) k_project_compact(ProjectArgs a) {
+  __shared__ uint8_t s_q1[PC_WARPS][PC_CHUNK];
+  __shared__ uint32_t s_q2[PC_WARPS][PC_CHUNK];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int base = (blockIdx.x * PC_WARPS + warp) * PC_CHUNK;
+  if (base >= a.P) return;
+  CamConst c;
+  load_cam(c, a.view, a.proj, a.campos);
+  const uint32_t lt = (1u << lane) - 1u;
+
+  // ---- stage 1: cull ----
+  uint32_t n1 = 0;
+  float vzs[PC_CHUNK / 32];
+#pragma unroll
+  for (int it = 0; it < PC_CHUNK / 32; it++) {
+    const int i = base + it * 32 + lane;
+    vzs[it] = -1.f;
+    if (i < a.P) {
+      const float mx = __ldg(a.means + 3 * (size_t)i), my = __ldg(a.means + 3 * (size_t)i + 1), mz = __ldg(a.means + 3 * (size_t)i + 2);
+      vzs[it] = c.v[2] * mx + c.v[6] * my + c.v[10] * mz + c.v[14];
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < PC_CHUNK / 32; it++) {
+    const int i = base + it * 32 + lane;
+    const bool pass = i < a.P && vzs[it] > a.near_plane;
+    if (i < a.P && !pass) { a.radii[i] = 0; a.depth_key[i] = 0xFFFFFFFFu; a.tiles[i] = 0u; }
+    const uint32_t m = __ballot_sync(0xffffffffu, pass);
+    if (pass) s_q1[warp][n1 + __popc(m & lt)] = (uint8_t)(it * 32 + lane);
+    n1 += __popc(m);
+  }
+  __syncwarp();
+
+  // ---- stage 2: geometry ----
+  uint32_t n2 = 0;
+  for (uint32_t k0 = 0; k0 < n1; k0 += 32) {
+    const bool on = k0 + lane < n1;
+    const int i = base + (on ? (int)s_q1[warp][k0 + lane] : 0);
+    uint32_t key = 0xFFFFFFFFu, ntiles = 0;
+    int radius = 0;
+    bool general = false;
+    if (on) {
+      const float3 mu = make_float3(__ldg(a.means + 3 * (size_t)i), __ldg(a.means + 3 * (size_t)i + 1), __ldg(a.means + 3 * (size_t)i + 2));
+      const float vz = c.v[2] * mu.x + c.v[6] * mu.y + c.v[10] * mu.z + c.v[14];
+      const float hx = c.p[0] * mu.x + c.p[4] * mu.y + c.p[8] * mu.z + c.p[12];
+      const float hy = c.p[1] * mu.x + c.p[5] * mu.y + c.p[9] * mu.z + c.p[13];
+      const float hw = c.p[3] * mu.x + c.p[7] * mu.y + c.p[11] * mu.z + c.p[15];
+      const float pw = 1.f / (hw + 0.0000001f);
+      const float ndcx = hx * pw, ndcy = hy * pw;
+      float c3[6];
+      if (a.cov3d_precomp) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) c3[k] = __ldg(a.cov3d_precomp + 6 * (size_t)i + k);
+      } else {
+        const float3 s = make_float3(__ldg(a.scales + 3 * (size_t)i), __ldg(a.scales + 3 * (size_t)i + 1), __ldg(a.scales + 3 * (size_t)i + 2));
+        const float4 q = __ldg(reinterpret_cast<const float4*>(a.rots) + i);
+        cov3d_from_scale_rot(s, a.scale_modifier, q, c3);
+      }
+      Ewa e;
+      ewa_jacobian(c, mu, (float)a.W, (float)a.H, a.tanfovx, a.tanfovy, e);
+      float ca, cb, cc;
+      cov2d(e, c3, ca, cb, cc);
+      const float det = ca * cc - cb * cb;
+      if (det != 0.f) {
+        const float det_inv = 1.f / det;
+        const float A = cc * det_inv, B = -cb * det_inv, C = ca * det_inv;
+        const float mid = 0.5f * (ca + cc);
+        const float disc = sqrtf(fmaxf(0.1f, mid * mid - det));
+        const float rad = ceilf(3.f * sqrtf(fmaxf(mid + disc, mid - disc)));
+        const float px = ((ndcx + 1.f) * a.W - 1.f) * 0.5f;
+        const float py = ((ndcy + 1.f) * a.H - 1.f) * 0.5f;
+        const int irad = (int)rad;
+        const TileRect r = reference_rect(px, py, irad, a.gx, a.gy);
+        if ((r.x1 - r.x0) * (r.y1 - r.y0) != 0) {
+          radius = irad;
+          const float o = __ldg(a.opac + i);
+          const float thr = __logf(255.f * o) + 0.01f;
+          uint32_t* cnt = nullptr;
+          if (a.bucket_count) {
+            const uint32_t db = __float_as_uint(vz);
+            const uint32_t rel = db > a.near_bits ? db - a.near_bits : 0u;
+            cnt = a.bucket_count + min(rel >> a.slice_shift, (1u << a.slices_log2) - 1u);
+          }
+          ntiles = (o > 0.f) ? count_tiles(px, py, A, B, C, thr, bin_rect(r, a.bin_shift), a.bin_shift, cnt, a.slices_log2, a.gbx) : 0u;
+          if (ntiles > 0) {
+            key = __float_as_uint(vz);
+            general = record_is_general(A, B, C, o);
+            float4* rec = a.rec + (size_t)i * REC_F4;
+            rec[0] = make_float4(px, py, A, B);
+            rec[1] = make_float4(C, o, thr, __uint_as_float((uint32_t)i));
+          }
+        }
+      }
+      a.radii[i] = radius;
+      a.depth_key[i] = key;
+      a.tiles[i] = ntiles;
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, ntiles > 0);
+    if (ntiles > 0) s_q2[warp][n2 + __popc(m & lt)] = (uint32_t)(i - base) | ((uint32_t)radius << 8) | (general ? 0x80000000u : 0u);
+    n2 += __popc(m);
+  }
+  __syncwarp();
+
+  // ---- stage 3: colour ----
+  for (uint32_t k0 = 0; k0 < n2; k0 += 32) {
+    if (k0 + lane >= n2) continue;
+    const uint32_t ent = s_q2[warp][k0 + lane];
+    const int i = base + (int)(ent & 255u);
+    const float frad = (ent >> 31) ? -(float)((ent >> 8) & 0x7FFFFFu) : (float)((ent >> 8) & 0x7FFFFFu);
+    float rgb[3];
+    uint32_t clampbits = 0;
+    if constexpr (DEG < 0) {
+      rgb[0] = __ldg(a.colors_precomp + 3 * (size_t)i);
+      rgb[1] = __ldg(a.colors_precomp + 3 * (size_t)i + 1);
+      rgb[2] = __ldg(a.colors_precomp + 3 * (size_t)i + 2);
+    } else {
+      constexpr int NB = (DEG < 0 ? 0 : (DEG + 1) * (DEG + 1));
+      constexpr int NF = NB * 3;
+      float f[NF > 0 ? NF : 1];
+      load_sh_row<NF>(a.shs + (size_t)i * a.M * 3, a.sh_vec != 0, f);
+      const float3 mu = make_float3(__ldg(a.means + 3 * (size_t)i), __ldg(a.means + 3 * (size_t)i + 1), __ldg(a.means + 3 * (size_t)i + 2));
+      float dx = mu.x - c.cam[0], dy = mu.y - c.cam[1], dz = mu.z - c.cam[2];
+      const float inv = 1.f / sqrtf(dx * dx + dy * dy + dz * dz);
+      float b[NB > 0 ? NB : 1];
+      sh_basis<DEG>(dx * inv, dy * inv, dz * inv, b);
+#pragma unroll
+      for (int ch = 0; ch < 3; ch++) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < NB; k++) acc += b[k] * f[3 * k + ch];
+        acc += 0.5f;
+        if (acc < 0.f) clampbits |= (1u << ch);
+        rgb[ch] = fmaxf(acc, 0.f);
+      }
+    }
+    a.clamped[i] = (uint8_t)clampbits;
+    a.rec[(size_t)i * REC_F4 + 2] = make_float4(rgb[0], rgb[1], rgb[2], frad);
+  }
 }
 
 // ==================================================================================================
@@ -755,8 +925,32 @@ __global__ void __launch_bounds__(256, PROJECT_BWD_MIN_BLOCKS) k_project_bwd(Pro
 }
 
 // ---- host launchers ------------------------------------------------------------------------------
+static std::atomic<int> g_project_mode{-1};
+void set_project_mode(int mode) { g_project_mode.store(mode == 1 ? 1 : 0); }
+static bool use_project_compact() {
+  int m = g_project_mode.load();
+  if (m < 0) {
+    const char* e = getenv("B200GS_PROJECT");
+    m = (e && e[0] == 'c') ? 1 : 0;      // B200GS_PROJECT=compact selects the dense-warp kernel (measured: no gain)
+    g_project_mode.store(m);
+  }
+  return m == 1;
+}
+
 void launch_project(const ProjectArgs& a, int deg, cudaStream_t st) {
   if (a.P == 0) return;
+  if (use_project_compact()) {
+    const dim3 grid((a.P + PC_CHUNK * PC_WARPS - 1) / (PC_CHUNK * PC_WARPS)), block(32 * PC_WARPS);
+    switch (deg) {
+      case -1: k_project_compact<-1><<<grid, block, 0, st>>>(a); break;
+      case 0: k_project_compact<0><<<grid, block, 0, st>>>(a); break;
+      case 1: k_project_compact<1><<<grid, block, 0, st>>>(a); break;
+      case 2: k_project_compact<2><<<grid, block, 0, st>>>(a); break;
+      default: k_project_compact<3><<<grid, block, 0, st>>>(a); break;
+    }
+    count_launch();
+    return;
+  }
   const dim3 grid((a.P + 255) / 256), block(256);
   switch (deg) {
     case -1: k_project<-1><<<grid, block, 0, st>>>(a); break;

@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(256) k_render_fwd(RenderArgs a) {
         const float4 q0 = st[j * REC_F4], q1 = st[j * REC_F4 + 1];
         hit = block_may_contribute(q0.x, q0.y, q0.z, q0.w, q1.x, q1.z, rx0, ry0, rx1, ry1);
         if (coarse && hit)
-          hit = tile_in_reference_rect(q0.x, q0.y, st[j * REC_F4 + 2].w, blockIdx.x, blockIdx.y, gridDim.x, gridDim.y);
+          hit = tile_in_reference_rect(q0.x, q0.y, fabsf(st[j * REC_F4 + 2].w), blockIdx.x, blockIdx.y, gridDim.x, gridDim.y);
       }
       uint32_t mask = __ballot_sync(0xffffffffu, hit);
       while (mask) {
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(256) k_render_bwd(RenderBwdArgs a) {
         const float4 q0 = st[j * REC_F4], q1 = st[j * REC_F4 + 1];
         hit = block_may_contribute(q0.x, q0.y, q0.z, q0.w, q1.x, q1.z, rx0, ry0, rx1, ry1);
         if (coarse && hit)
-          hit = tile_in_reference_rect(q0.x, q0.y, st[j * REC_F4 + 2].w, blockIdx.x, blockIdx.y, gridDim.x, gridDim.y);
+          hit = tile_in_reference_rect(q0.x, q0.y, fabsf(st[j * REC_F4 + 2].w), blockIdx.x, blockIdx.y, gridDim.x, gridDim.y);
       }
       uint32_t mask = __ballot_sync(0xffffffffu, hit);
       while (mask) {

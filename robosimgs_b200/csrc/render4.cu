@@ -98,10 +98,12 @@ __global__ void __launch_bounds__(R4_THREADS, R4_FWD_MINB) k_render_fwd4(RenderA
     nstop[2 * h] = n; nstop[2 * h + 1] = n;
   }
 
-  // One record against the thread's four pixels.  CLAMP = false when opacity <= 0.99: then
-  // min(0.99, o*G) is the identity for every pair that can pass the tests (G <= 1 when power <= 0).
+  // One record against the thread's four pixels.  CLAMP = false for unmarked records (opacity <= 0.99 and a safely
+  // positive definite conic): then power <= 0 for every pixel, G <= 1 and min(0.99, o*G) is the identity.
   // The accumulate is predicated, not selected: FSETP/FSEL/FMNMX share the half-rate ALU pipe, which
   // co-limits this loop with the issue rate (ncu: math-pipe throttle).
+  // GENERAL = the record is marked (negative radius, project.cu:record_is_general): clamp alpha at 0.99 and skip
+  // pixels whose power rounds above 0.  Unmarked records can do neither, so both tests are dropped for them.
   auto eval = [&](const float4& q0, const float4& q1, const float4& q2, uint32_t pos, auto clamp_tag) {
     constexpr bool CLAMP = decltype(clamp_tag)::value;
     const RowTerms rt = row_terms(q0.z, q0.w, q1.x, q0.y - t.pyf);
@@ -116,8 +118,8 @@ __global__ void __launch_bounds__(R4_THREADS, R4_FWD_MINB) k_render_fwd4(RenderA
       float2 alpha = __fmul2_rn(o2, make_float2(ex2_fast(p2.x), ex2_fast(p2.y)));
       if (CLAMP) alpha = make_float2(fminf(0.99f, alpha.x), fminf(0.99f, alpha.y));
       const float2 test_T = __fmul2_rn(T[h], __ffma2_rn(alpha, make_float2(-1.f, -1.f), make_float2(1.f, 1.f)));
-      const bool valid0 = p2.x <= 0.f && alpha.x >= (1.f / 255.f);
-      const bool valid1 = p2.y <= 0.f && alpha.y >= (1.f / 255.f);
+      const bool valid0 = (!CLAMP || p2.x <= 0.f) && alpha.x >= (1.f / 255.f);
+      const bool valid1 = (!CLAMP || p2.y <= 0.f) && alpha.y >= (1.f / 255.f);
       const bool upd0 = valid0 && test_T.x >= 0.0001f, upd1 = valid1 && test_T.y >= 0.0001f;
       stop[2 * h] = valid0 && !(test_T.x >= 0.0001f);
       stop[2 * h + 1] = valid1 && !(test_T.y >= 0.0001f);
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(R4_THREADS, R4_FWD_MINB) k_render_fwd4(RenderA
         const float4 q0 = st[j * REC_F4], q1 = st[j * REC_F4 + 1];
         hit = r4_block_may_contribute(q0.x, q0.y, q0.z, q0.w, q1.x, q1.z, t.rx0, t.ry0, t.rx1, t.ry1);
         if (coarse && hit)
-          hit = r4_tile_in_reference_rect(q0.x, q0.y, st[j * REC_F4 + 2].w, blockIdx.x, blockIdx.y, gridDim.x,
+          hit = r4_tile_in_reference_rect(q0.x, q0.y, fabsf(st[j * REC_F4 + 2].w), blockIdx.x, blockIdx.y, gridDim.x,
                                           gridDim.y);
       }
       uint32_t mask = __ballot_sync(0xffffffffu, hit);
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(R4_THREADS, R4_FWD_MINB) k_render_fwd4(RenderA
         const uint32_t jj = base + b;
         const float4 q0 = st[jj * REC_F4], q1 = st[jj * REC_F4 + 1], q2 = st[jj * REC_F4 + 2];
         const uint32_t pos = c * R4_CH + jj;
-        if (q1.y > 0.99f) eval(q0, q1, q2, pos, std::true_type{});
+        if (q2.w < 0.f) eval(q0, q1, q2, pos, std::true_type{});
         else eval(q0, q1, q2, pos, std::false_type{});
       }
     }
@@ -335,7 +337,7 @@ __global__ void __launch_bounds__(R4_THREADS, R4_BWD_MINB) k_render_bwd4(RenderB
         const float4 q0 = st[j * REC_F4], q1 = st[j * REC_F4 + 1];
         hit = r4_block_may_contribute(q0.x, q0.y, q0.z, q0.w, q1.x, q1.z, t.rx0, t.ry0, t.rx1, t.ry1);
         if (coarse && hit)
-          hit = r4_tile_in_reference_rect(q0.x, q0.y, st[j * REC_F4 + 2].w, blockIdx.x, blockIdx.y, gridDim.x,
+          hit = r4_tile_in_reference_rect(q0.x, q0.y, fabsf(st[j * REC_F4 + 2].w), blockIdx.x, blockIdx.y, gridDim.x,
                                           gridDim.y);
       }
       uint32_t mask = __ballot_sync(0xffffffffu, hit);

@@ -119,7 +119,7 @@ def test_c3_radii_alpha_and_projection_fields_match_oracle(c3):
     opac = np.abs(rec[live, 5] - con[:, 3]).max()
     rgb = np.abs(rec[live, 8:11] - st64.rgb[live]).max()
     idx_ok = bool((rec[live, 7].view(np.uint32) == np.nonzero(live)[0].astype(np.uint32)).all())
-    rad_ok = float((rec[live, 11].astype(np.int32) == radii[live]).mean())
+    rad_ok = float((np.abs(rec[live, 11]).astype(np.int32) == radii[live]).mean())     # sign = "general record" mark
     d32 = st32.depths.astype(np.float32).view(np.uint32)
     depth_ulps = np.abs(depth_bits[live].astype(np.int64) - d32[live].astype(np.int64)).max()
     cl_o = (st32.clamped[:, 0] | (st32.clamped[:, 1] << 1) | (st32.clamped[:, 2] << 2)).astype(np.uint8)
