@@ -356,18 +356,25 @@ __global__ void __launch_bounds__(R4_THREADS, R4_BWD_MINB) k_render_bwd4(RenderB
         const float2 o2 = make_float2(q1.y, q1.y);
         float2 ndx[2], G[2], alpha[2], vmask[2];
         bool any_valid = false;
+        // marked records (negative radius, project.cu:record_is_general) clamp alpha at 0.99 and skip pixels whose
+        // power rounds above 0; for all others neither can happen and both tests are dropped (as in the forward)
+        auto alphas = [&](auto general_tag) {
+          constexpr bool GENERAL = decltype(general_tag)::value;
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-          ndx[h] = __fadd2_rn(pxf2[h], nx2);
-          const float2 p2 = __ffma2_rn(ndx[h], __ffma2_rn(nhA2, ndx[h], bdy2), ncdy2);
-          G[h] = make_float2(ex2_fast(p2.x), ex2_fast(p2.y));
-          const float2 og = __fmul2_rn(o2, G[h]);
-          alpha[h] = make_float2(fminf(0.99f, og.x), fminf(0.99f, og.y));
-          const bool v0 = pos < nc[2 * h] && p2.x <= 0.f && alpha[h].x >= (1.f / 255.f);
-          const bool v1 = pos < nc[2 * h + 1] && p2.y <= 0.f && alpha[h].y >= (1.f / 255.f);
-          vmask[h] = make_float2(v0 ? 1.f : 0.f, v1 ? 1.f : 0.f);
-          any_valid = any_valid || v0 || v1;
-        }
+          for (int h = 0; h < 2; h++) {
+            ndx[h] = __fadd2_rn(pxf2[h], nx2);
+            const float2 p2 = __ffma2_rn(ndx[h], __ffma2_rn(nhA2, ndx[h], bdy2), ncdy2);
+            G[h] = make_float2(ex2_fast(p2.x), ex2_fast(p2.y));
+            const float2 og = __fmul2_rn(o2, G[h]);
+            alpha[h] = GENERAL ? make_float2(fminf(0.99f, og.x), fminf(0.99f, og.y)) : og;
+            const bool v0 = pos < nc[2 * h] && (!GENERAL || p2.x <= 0.f) && alpha[h].x >= (1.f / 255.f);
+            const bool v1 = pos < nc[2 * h + 1] && (!GENERAL || p2.y <= 0.f) && alpha[h].y >= (1.f / 255.f);
+            vmask[h] = make_float2(v0 ? 1.f : 0.f, v1 ? 1.f : 0.f);
+            any_valid = any_valid || v0 || v1;
+          }
+        };
+        if (q2.w < 0.f) alphas(std::true_type{});
+        else alphas(std::false_type{});
         if (!__any_sync(0xffffffffu, any_valid)) continue;
         const float2 one2 = make_float2(1.f, 1.f), neg2 = make_float2(-1.f, -1.f);
         const float2 cr2 = make_float2(q2.x, q2.x), cg2 = make_float2(q2.y, q2.y), cb2 = make_float2(q2.z, q2.z);
