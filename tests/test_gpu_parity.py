@@ -620,3 +620,30 @@ def test_dense_warp_projection_kernels_are_bit_identical(degree, precomp):
     finally:
         _cabi.set_option("project", 0)
         _cabi.set_option("binning", -1)
+
+
+@pytest.mark.parametrize("W,H,shift,expect_bucketed", [(512, 512, 0, True), (1104, 1104, 0, False), (1920, 1080, 1, False),
+                                                       (1920, 1080, 2, True)])
+def test_bin_count_limits_of_the_bucketed_binning(W, H, shift, expect_bucketed):
+    """The bucket scan runs one CTA per bin with a look-back over the lower bins and is used up to 1024 bins
+    (512 slices each at the limit); images with more bins take the library-sort pipeline.  Both sides of the limit
+    against the oracle, and the many-bin look-back (1024 CTAs) against the few-bin one, bit for bit."""
+    from robosimgs_b200 import _cabi
+    from robosimgs_b200.cameras import camera_look_at
+    from robosimgs_b200.scenes import cube_scene, settings_from_camera
+    bins = -(-((W + 15) // 16) // (1 << shift)) * -(-((H + 15) // 16) // (1 << shift))
+    assert (bins <= 1024) == expect_bucketed
+    sc, _ = cube_scene(P=20000, seed=9, degree=1)
+    cam = camera_look_at((0.4, 0.3, 3.2), (0, 0, 0), (0, 1, 0), 55.0, W, H)
+    rs = settings_from_camera(cam, 1, bg=(0.1, 0.2, 0.3))
+    try:
+        _cabi.set_option("bin_shift", shift)
+        color, radii, _ = gpu_render(sc, cam, 1, bg=(0.1, 0.2, 0.3))
+        _cabi.set_option("bin_shift", 3)
+        color3, _, _ = gpu_render(sc, cam, 1, bg=(0.1, 0.2, 0.3))
+    finally:
+        _cabi.set_option("bin_shift", -1)
+    assert np.array_equal(color, color3)
+    st = _oracle(rs, sc, np.float32)
+    assert psnr(color, st.color) >= PSNR_MIN
+    assert (radii != st.radii).mean() <= 1e-3
