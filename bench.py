@@ -302,7 +302,8 @@ def run_b200(args):
     _cabi.profile_read(reset=True)
     _cabi.launch_count(reset=True)
     with torch.no_grad():
-        serial_ms = timed(lambda s: render(settings_dev[Wm + s]), K)
+        serial_runs = [timed(lambda s: render(settings_dev[Wm + s]), K) for _ in range(R)]
+        serial_ms = statistics.median(serial_runs)
     if args.streams <= 1:
         fwd_ms, fwd_runs, launches = serial_ms, [serial_ms], _cabi.launch_count(reset=False)
     _cabi.launch_count(reset=True)
@@ -429,6 +430,7 @@ def run_b200(args):
         "timed_frames": K * R,
         "frame_latency_ms": serial_ms / K,
         "single_stream": {"ms_per_frame": serial_ms / K, "mpixels_per_s": px / (serial_ms / K * 1e-3) / 1e6,
+                          "ms_per_frame_runs": [round(t / K, 5) for t in serial_runs],
                           "what": "SURVEY 8(d) definition: W*H / t_fwd with every frame issued on ONE stream through "
                                   "GaussianRasterizer.forward (no graphs, no frames in flight); `value` is the sweep rate"},
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

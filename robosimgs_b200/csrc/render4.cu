@@ -153,6 +153,8 @@ __global__ void __launch_bounds__(R4_THREADS, R4_FWD_MINB) k_render_fwd4(RenderA
   for (; c < nchunks; c++) {
     ring.wait(c);
     const uint32_t cnt = ring.count(c);
+    r4_prescale(sm[c % R4_STAGES], cnt, tid);
+    __syncthreads();
     const float4* st = sm[c % R4_STAGES];
     for (uint32_t base = 0; base < cnt; base += 32) {
       if (__all_sync(0xffffffffu, all_done())) break;
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(R4_THREADS, R4_FWD_MINB) k_render_fwd4(RenderA
       bool hit = false;
       if (j < cnt) {
         const float4 q0 = st[j * REC_F4], q1 = st[j * REC_F4 + 1];
-        hit = r4_block_may_contribute(q0.x, q0.y, q0.z, q0.w, q1.x, q1.z, t.rx0, t.ry0, t.rx1, t.ry1);
+        hit = r4_block_may_contribute_scaled(q0.x, q0.y, q0.z, q0.w, q1.x, q1.z, t.rx0, t.ry0, t.rx1, t.ry1);
         if (coarse && hit)
           hit = r4_tile_in_reference_rect(q0.x, q0.y, fabsf(st[j * REC_F4 + 2].w), blockIdx.x, blockIdx.y, gridDim.x,
                                           gridDim.y);
@@ -328,6 +330,8 @@ __global__ void __launch_bounds__(R4_THREADS, R4_BWD_MINB) k_render_bwd4(RenderB
   for (; c < nchunks; c++) {
     ring.wait(c);
     const uint32_t cnt = ring.count(c);
+    r4_prescale(sm[c % R4_STAGES], cnt, tid);
+    __syncthreads();
     const float4* st = sm[c % R4_STAGES];
     for (uint32_t base = 0; base < cnt; base += 32) {
       if (__all_sync(0xffffffffu, c * R4_CH + base >= ncmax)) break;
@@ -335,7 +339,7 @@ __global__ void __launch_bounds__(R4_THREADS, R4_BWD_MINB) k_render_bwd4(RenderB
       bool hit = false;
       if (j < cnt) {
         const float4 q0 = st[j * REC_F4], q1 = st[j * REC_F4 + 1];
-        hit = r4_block_may_contribute(q0.x, q0.y, q0.z, q0.w, q1.x, q1.z, t.rx0, t.ry0, t.rx1, t.ry1);
+        hit = r4_block_may_contribute_scaled(q0.x, q0.y, q0.z, q0.w, q1.x, q1.z, t.rx0, t.ry0, t.rx1, t.ry1);
         if (coarse && hit)
           hit = r4_tile_in_reference_rect(q0.x, q0.y, fabsf(st[j * REC_F4 + 2].w), blockIdx.x, blockIdx.y, gridDim.x,
                                           gridDim.y);

@@ -31,6 +31,36 @@ __device__ __forceinline__ bool r4_block_may_contribute(float x, float y, float 
   return 0.5f * q - 4e-6f * mag <= thr;
 }
 
+// The same test on a record whose conic was pre-scaled for the exp2 evaluation (r4_prescale): hA = A log2(e)/2,
+// Bs = B log2(e), hC = C log2(e)/2, thr2 = thr log2(e).  0.5 q log2(e) = hA dx^2 + Bs dx dy + hC dy^2, B/C = Bs/(2 hC).
+__device__ __forceinline__ bool r4_block_may_contribute_scaled(float x, float y, float hA, float Bs, float hC, float thr2,
+                                                               float x0, float y0, float x1, float y1) {
+  const float cx = clampf(x, x0, x1), cy = clampf(y, y0, y1);
+  const float dxe = cx - x, dye = cy - y;
+  float dy1 = clampf(y - 0.5f * Bs * dxe * rcp_fast(hC), y0, y1) - y;
+  const float q1 = hA * dxe * dxe + Bs * dxe * dy1 + hC * dy1 * dy1;
+  float dx2 = clampf(x - 0.5f * Bs * dye * rcp_fast(hA), x0, x1) - x;
+  const float q2 = hA * dx2 * dx2 + Bs * dx2 * dye + hC * dye * dye;
+  const float q = fminf(q1, q2);
+  const float mag = fabsf(hA) * (dxe * dxe + dx2 * dx2) + fabsf(hC) * (dye * dye + dy1 * dy1);
+  return q - 8e-6f * mag <= thr2;
+}
+
+// One thread per record of a freshly landed ring stage: scale the conic (and the culling threshold) in place, ONCE,
+// with exactly the products row_terms() used to form per record and per warp -- so the evaluation below is unchanged
+// bit for bit and three multiplies per record leave the hot loop.  The caller synchronises the CTA afterwards.
+__device__ __forceinline__ void r4_prescale(float4* st, uint32_t cnt, int tid) {
+  if ((uint32_t)tid < cnt) {
+    float4 q0 = st[tid * REC_F4], q1 = st[tid * REC_F4 + 1];
+    q0.z = __fmul_rn(q0.z, 0.5f * LOG2E);
+    q0.w = __fmul_rn(q0.w, LOG2E);
+    q1.x = __fmul_rn(q1.x, 0.5f * LOG2E);
+    q1.z = __fmul_rn(q1.z, LOG2E);
+    st[tid * REC_F4] = q0;
+    st[tid * REC_F4 + 1] = q1;
+  }
+}
+
 __device__ __forceinline__ bool r4_tile_in_reference_rect(float px, float py, float fr, int tx, int ty, int gx,
                                                           int gy) {
   const int x0 = min(gx, max(0, (int)((px - fr) / TILE)));
@@ -111,6 +141,8 @@ struct Ring4Slab {
   __device__ __forceinline__ void issue(uint32_t c) {
     if (tid == 0 && c < nchunks) {
       const uint32_t bytes = count(c) * (uint32_t)(REC_F4 * sizeof(float4));
+      // the stage was written through the generic proxy (r4_prescale): order those writes before the bulk copy
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_expect_tx(&bar[c % R4_STAGES], bytes);
       tma_load_1d(&sm[c % R4_STAGES][0], slab + (size_t)c * R4_CH * REC_F4, bytes, &bar[c % R4_STAGES]);
     }
@@ -138,11 +170,12 @@ struct Ring4Slab {
 struct RowTerms {
   float hA, bdy, cdy2;
 };
-__device__ __forceinline__ RowTerms row_terms(float A, float B, float C, float dy) {
+// from a PRE-SCALED record (r4_prescale): hA = A log2(e)/2 as stored, bdy = (B log2(e)) dy, cdy2 = ((C log2(e)/2) dy) dy
+__device__ __forceinline__ RowTerms row_terms(float hA, float Bs, float hC, float dy) {
   RowTerms r;
-  r.hA = __fmul_rn(A, 0.5f * LOG2E);
-  r.bdy = __fmul_rn(__fmul_rn(B, LOG2E), dy);
-  r.cdy2 = __fmul_rn(__fmul_rn(__fmul_rn(C, 0.5f * LOG2E), dy), dy);
+  r.hA = hA;
+  r.bdy = __fmul_rn(Bs, dy);
+  r.cdy2 = __fmul_rn(__fmul_rn(hC, dy), dy);
   return r;
 }
 __device__ __forceinline__ float power2_of(const RowTerms& r, float dx) {
