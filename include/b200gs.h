@@ -289,7 +289,9 @@ int b200gs_buffer_sizes(int32_t P, int32_t image_height, int32_t image_width, in
  * test or a debugger compare the projection stage field by field without the library
  * exposing its scratch as API.  offsets[0] rec: float[P][12] = {x, y, conic A, B | C, opacity, threshold,
  * index bits | r, g, b, radius}, written only for Gaussians that touch a bin; [1] depth_key: uint32[P] IEEE bits
- * of the view-space depth (0xFFFFFFFF = culled); [2] tiles: uint32[P] bins touched; [3] offsets: uint32[P]
+ * of the view-space depth (0xFFFFFFFF = culled); [2] tiles: uint32[P] bins touched (0 = none; with the bucketed binning
+ * and at most 255 bins a footprint of 1..3 bins is stored packed: bit 31 set, count in bits 24..25, bin ids in the
+ * low three bytes); [3] offsets: uint32[P]
  * inclusive scan of tiles (global-sort pipeline only); [4] clamped: uint8[P], bit c = colour channel c was
  * clamped at 0. */
 #define B200GS_GEOM_FIELDS 5

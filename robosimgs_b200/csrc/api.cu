@@ -443,6 +443,7 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
   pa.slices_log2 = slices_log2;
   pa.slice_shift = 27 - slices_log2;      // 16 octaves of depth from the near plane over 2^slices_log2 slices
   pa.near_bits = near_bits;
+  pa.pack_tiles = (bucketed && num_tiles <= 255) ? 1 : 0;
   // bucket counters and, directly in front of them, the look-back words of the bucket scan
   if (bucketed && P > 0 &&
       (rc = check_cuda(cudaMemsetAsync(ib.bin_pub, 0, sizeof(unsigned long long) * BUCKET_BINS_MAX +

@@ -164,7 +164,8 @@ __global__ void __launch_bounds__(32 * EMIT_WARPS) k_emit_bucket(BucketArgs a) {
   __shared__ uint32_t stage[EMIT_WARPS][EMIT_STAGE];
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t n = (r < a.P) ? a.tiles[r] : 0u;
+  const uint32_t tword = (r < a.P) ? a.tiles[r] : 0u;     // count, or a packed footprint of up to three bins
+  uint32_t n = tiles_count(tword);
   const uint32_t big_lanes = __ballot_sync(0xffffffffu, n > BUCKET_BIG_THRESHOLD);
   if (n > BUCKET_BIG_THRESHOLD) n = 0;          // large footprints: emitted by the whole warp below
   uint32_t incl = n;
@@ -176,7 +177,12 @@ __global__ void __launch_bounds__(32 * EMIT_WARPS) k_emit_bucket(BucketArgs a) {
   const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
   if (total == 0 && big_lanes == 0u) return;
   uint32_t rel = 0;
-  if (n) {
+  if (n && (tword & TILES_PACKED)) {
+    // small footprint: the projection kernel left the bin ids in tiles[] -- no record load, no span arithmetic
+    rel = rel_depth(a, a.depth_key[r]);
+    uint32_t o = incl - n;
+    for (uint32_t k = 0; k < n; k++, o++) stage[warp][o] = ((tword >> (8u * k)) & 0xFFu) | ((uint32_t)lane << 16);
+  } else if (n) {
     rel = rel_depth(a, a.depth_key[r]);
     const float4 q0 = a.rec[(size_t)r * REC_F4], q1 = a.rec[(size_t)r * REC_F4 + 1];
     const TileRect rect = bin_rect(reference_rect(q0.x, q0.y, a.radii[r], a.gx, a.gy), a.bin_shift);

@@ -16,6 +16,7 @@ struct ProjectArgs {
   uint32_t* bucket_count;  // bucketed binning: per-(bin, depth slice) pair counters, else nullptr
   int slices_log2, slice_shift;   // slice = min((depth bits - near_bits) >> slice_shift, 2^slices_log2 - 1)
   uint32_t near_bits;
+  int pack_tiles;          // bucketed binning with <= 255 bins: tiles[] carries small footprints packed (spans.cuh)
   float tanfovx, tanfovy, scale_modifier, near_plane;
   const float *means, *scales, *rots, *opac, *shs, *colors_precomp, *cov3d_precomp;
   const float *view, *proj, *campos;

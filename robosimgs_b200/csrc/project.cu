@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(256, PROJECT_MIN_BLOCKS) k_project(ProjectArgs
   CamConst c;
   load_cam(c, a.view, a.proj, a.campos);
 
-  uint32_t key = 0xFFFFFFFFu, ntiles = 0;
+  uint32_t key = 0xFFFFFFFFu, ntiles = 0, tiles_word = 0;
   int radius = 0;
 
   const float3 mu = make_float3(__ldg(a.means + 3 * i), __ldg(a.means + 3 * i + 1), __ldg(a.means + 3 * i + 2));
@@ -224,7 +224,8 @@ __global__ void __launch_bounds__(256, PROJECT_MIN_BLOCKS) k_project(ProjectArgs
           const uint32_t rel = db > a.near_bits ? db - a.near_bits : 0u;
           cnt = a.bucket_count + min(rel >> a.slice_shift, (1u << a.slices_log2) - 1u);
         }
-        ntiles = (o > 0.f) ? count_tiles(px, py, A, B, C, thr, bin_rect(r, a.bin_shift), a.bin_shift, cnt, a.slices_log2, a.gbx) : 0u;
+        ntiles = (o > 0.f) ? count_tiles(px, py, A, B, C, thr, bin_rect(r, a.bin_shift), a.bin_shift, cnt, a.slices_log2, a.gbx,
+                                         a.pack_tiles != 0, &tiles_word) : 0u;
         if (ntiles > 0) {
           float rgb[3];
           uint32_t clampbits = 0;
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(256, PROJECT_MIN_BLOCKS) k_project(ProjectArgs
   }
   a.radii[i] = radius;
   a.depth_key[i] = key;
-  a.tiles[i] = ntiles;
+  a.tiles[i] = tiles_word;
 }
 
 // ==================================================================================================
@@ -322,7 +323,7 @@ __global__ void __launch_bounds__(32 * PC_WARPS) k_project_compact(ProjectArgs a
   for (uint32_t k0 = 0; k0 < n1; k0 += 32) {
     const bool on = k0 + lane < n1;
     const int i = base + (on ? (int)s_q1[warp][k0 + lane] : 0);
-    uint32_t key = 0xFFFFFFFFu, ntiles = 0;
+    uint32_t key = 0xFFFFFFFFu, ntiles = 0, tiles_word = 0;
     int radius = 0;
     bool general = false;
     if (on) {
@@ -367,7 +368,8 @@ __global__ void __launch_bounds__(32 * PC_WARPS) k_project_compact(ProjectArgs a
             const uint32_t rel = db > a.near_bits ? db - a.near_bits : 0u;
             cnt = a.bucket_count + min(rel >> a.slice_shift, (1u << a.slices_log2) - 1u);
           }
-          ntiles = (o > 0.f) ? count_tiles(px, py, A, B, C, thr, bin_rect(r, a.bin_shift), a.bin_shift, cnt, a.slices_log2, a.gbx) : 0u;
+          ntiles = (o > 0.f) ? count_tiles(px, py, A, B, C, thr, bin_rect(r, a.bin_shift), a.bin_shift, cnt, a.slices_log2, a.gbx,
+                                           a.pack_tiles != 0, &tiles_word) : 0u;
           if (ntiles > 0) {
             key = __float_as_uint(vz);
             general = record_is_general(A, B, C, o);
@@ -379,7 +381,7 @@ __global__ void __launch_bounds__(32 * PC_WARPS) k_project_compact(ProjectArgs a
       }
       a.radii[i] = radius;
       a.depth_key[i] = key;
-      a.tiles[i] = ntiles;
+      a.tiles[i] = tiles_word;
     }
     const uint32_t m = __ballot_sync(0xffffffffu, ntiles > 0);
     if (ntiles > 0) s_q2[warp][n2 + __popc(m & lt)] = (uint32_t)(i - base) | ((uint32_t)radius << 8) | (general ? 0x80000000u : 0u);
@@ -678,7 +680,7 @@ __global__ void __launch_bounds__(256, PROJECT_BWD_MIN_BLOCKS) k_project_bwd(Pro
   float gq[4] = {0.f, 0.f, 0.f, 0.f};
   float g2x = 0.f, g2y = 0.f, gop = 0.f;
   float gcol[3] = {0.f, 0.f, 0.f};
-  const bool active = in_range && a.radii[i] > 0 && a.tiles[i] > 0;
+  const bool active = in_range && a.radii[i] > 0 && a.tiles[i] != 0u;     // (tiles[] may hold a packed footprint)
   const bool vec_ok = a.sh_vec != 0;
 
   if (active) {

@@ -116,22 +116,34 @@ __device__ __forceinline__ void row_span(const SpanCtx& s, const TileRect& r, in
 
 // Number of bins the splat touches.  With bucket_count != nullptr (bucketed binning, bucket.cu) the pair counter
 // of every touched bin's bucket is incremented as well (one RED per pair): bucket_count already points at the
-// splat's depth slice, the buckets of one bin are `bucket_stride` counters apart.
+// splat's depth slice, the buckets of one bin are `bucket_stride` counters apart.  *packed (bucketed binning with at
+// most 255 bins only) receives the footprint in the form the emission kernel reads back from tiles[]:
+//   TILES_PACKED | b2 << 16 | b1 << 8 | b0 with count = number of bins (1..3) in bits 24..25  -- small footprints,
+//   the plain count otherwise (emission recomputes the spans).
+constexpr uint32_t TILES_PACKED = 0x80000000u;
+__device__ __forceinline__ uint32_t tiles_count(uint32_t t) { return (t & TILES_PACKED) ? (t >> 24) & 3u : t; }
+
 __device__ __forceinline__ uint32_t count_tiles(float x, float y, float A, float B, float C, float thr,
                                                 const TileRect& r, int bin_shift, uint32_t* bucket_count,
-                                                int bucket_stride_log2, int gbx) {
+                                                int bucket_stride_log2, int gbx, bool pack, uint32_t* packed) {
   SpanCtx s;
+  *packed = 0u;
   if (!span_setup(s, x, y, A, B, C, thr, r, bin_shift)) return 0;
-  uint32_t n = 0;
+  uint32_t n = 0, ids = 0;
   for (int ty = s.ty0; ty < s.ty1; ty++) {
     int c0, c1;
     row_span(s, r, ty, c0, c1);
-    n += (uint32_t)(c1 - c0);
     if (bucket_count)
-      for (int tx = c0; tx < c1; tx++) atomicAdd(bucket_count + ((size_t)(ty * gbx + tx) << bucket_stride_log2), 1u);
+      for (int tx = c0; tx < c1; tx++) {
+        const uint32_t bin = (uint32_t)(ty * gbx + tx);
+        atomicAdd(bucket_count + ((size_t)bin << bucket_stride_log2), 1u);
+        const uint32_t k = n + (uint32_t)(tx - c0);
+        if (k < 3u) ids |= bin << (8u * k);
+      }
+    n += (uint32_t)(c1 - c0);
   }
+  *packed = (pack && n >= 1u && n <= 3u) ? (TILES_PACKED | (n << 24) | ids) : n;
   return n;
 }
-
 
 }  // namespace b200gs
