@@ -334,7 +334,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cameras", type=int, default=64)
     ap.add_argument("--gaussians", type=int, default=3_000_000)
-    ap.add_argument("--streams", type=int, default=4)
+    ap.add_argument("--streams", type=int, default=6)
     ap.add_argument("--repeat", type=int, default=4, help="passes over this rank's cameras inside the timed region")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
