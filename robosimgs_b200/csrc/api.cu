@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <atomic>
 #include <functional>
 #include <mutex>
@@ -429,8 +430,11 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
   pa.clamped = gb.clamped;
   // bucketed binning: at most BUCKET_BINS_MAX bins (one scan CTA each, look-back over the lower bins)
   const bool bucketed = use_bucketed() && (uint32_t)num_tiles <= BUCKET_BINS_MAX;
+  // depth slices per bin: as many as the bucket tables hold, but no more buckets than ~4 per Gaussian (a 10 k-Gaussian
+  // scene must not clear and scan half a million counters)
+  const uint32_t bucket_budget = (uint32_t)std::min<uint64_t>(BUCKETS_MAX, std::max<uint64_t>(4ull * (uint64_t)P, 4096ull));
   int slices_log2 = 2;
-  while (bucketed && slices_log2 < BUCKET_SLICES_LOG2_MAX && ((uint32_t)num_tiles << (slices_log2 + 1)) <= BUCKETS_MAX)
+  while (bucketed && slices_log2 < BUCKET_SLICES_LOG2_MAX && ((uint32_t)num_tiles << (slices_log2 + 1)) <= bucket_budget)
     slices_log2++;
   const uint32_t num_buckets = (uint32_t)num_tiles << slices_log2;
   uint32_t near_bits;
@@ -464,7 +468,7 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
   ba.tiles = gb.tiles; ba.depth_key = gb.depth_key; ba.rec = gb.rec; ba.radii = radii;
   ba.bucket_count = ib.bucket_count; ba.bucket_base = ib.bucket_base; ba.bucket_cursor = ib.bucket_cursor;
   ba.bin_pub = ib.bin_pub; ba.ranges = ib.ranges;
-  ba.total = gb.counters + 1; ba.big_queue = gb.big_queue; ba.big_count = gb.counters;
+  ba.total = gb.counters + 1;
   ba.big_seg_count = gb.counters + 2; ba.total_windows = gb.counters + 3;
   ba.win_first = nullptr; ba.win_capacity = 0; ba.big_segs = nullptr;
   ba.seg = nullptr; ba.seg_alt = nullptr; ba.vals_sorted = nullptr; ba.slab = nullptr;
@@ -499,7 +503,7 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
         (rc2 = check_cuda(cudaMemsetAsync(ib.ranges, 0, sizeof(uint2) * (size_t)num_tiles, st), "clear ranges")))
       return rc2;
     if (cap > 0 && bucketed) {
-      // queue lengths (large-footprint Gaussians, large segments) and window count; counters[1] = D is rewritten
+      // queue length of the large segments and window count; counters[1] = D is rewritten by the scan
       if ((rc2 = check_cuda(cudaMemsetAsync(gb.counters, 0, 4 * sizeof(uint32_t), st), "clear queue lengths"))) return rc2;
       if (!bin_pub_clean &&
           (rc2 = check_cuda(cudaMemsetAsync(ib.bin_pub, 0, sizeof(unsigned long long) * (size_t)num_tiles, st),

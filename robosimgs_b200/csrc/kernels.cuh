@@ -57,7 +57,6 @@ struct BucketArgs {
   uint32_t* bucket_cursor;            // [num_bins << slices_log2] append cursors (start at bucket_base)
   uint2* ranges;                      // [num_bins] per-bin [start,end) into vals_sorted
   uint32_t* total;                    // D
-  uint32_t *big_queue, *big_count;    // large-footprint Gaussians (emitted one warp each)
   unsigned long long* bin_pub;        // [num_bins] look-back words of the scan (valid | windows << 32 | pairs), zeroed
   uint32_t* win_first;                // [capacity / BUCKET_WINDOW + num_bins + 2] first bucket of every sort window
   uint32_t win_capacity;              // entries of win_first
