@@ -5,7 +5,7 @@ torch restatement (forward, fp64) and structural invariants of the binning; GPU:
 import numpy as np
 import pytest
 import torch
-from hypothesis import HealthCheck, given, settings, strategies as st
+from hypothesis import HealthCheck, example, given, settings, strategies as st
 
 from oracle import gs_oracle, gs_oracle_torch
 from helpers import psnr
@@ -41,7 +41,7 @@ scene_args = dict(seed=st.integers(0, 2**31 - 1), P=st.sampled_from([0, 1, 2, 17
                   fov=st.sampled_from([35.0, 70.0, 110.0]))
 
 
-@settings(max_examples=25, deadline=None, suppress_health_check=list(HealthCheck))
+@settings(max_examples=25, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
 @given(**scene_args)
 def test_oracle_forward_equals_its_torch_restatement_on_edge_cases(seed, P, degree, spread, lo, hi_add, opac_kind, aniso, W, H, fov):
     sc = _scene(seed, P, degree, spread, lo, lo + hi_add, opac_kind, aniso)
@@ -72,8 +72,9 @@ def test_oracle_forward_equals_its_torch_restatement_on_edge_cases(seed, P, degr
 
 
 @pytest.mark.gpu
-@settings(max_examples=20, deadline=None, suppress_health_check=list(HealthCheck))
+@settings(max_examples=40, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
 @given(**scene_args)
+@example(seed=1, P=17, degree=0, spread=2.5, lo=-4.0, hi_add=1.5, opac_kind="uniform", aniso=30.0, W=16, H=16, fov=35.0)
 def test_cuda_matches_oracle_on_edge_cases(built, seed, P, degree, spread, lo, hi_add, opac_kind, aniso, W, H, fov):
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
@@ -93,7 +94,13 @@ def test_cuda_matches_oracle_on_edge_cases(built, seed, P, degree, spread, lo, h
         return
     assert ((radii > 0) != (stt.radii > 0)).mean() <= 0.02
     ref = gs_oracle.backward(stt, w.numpy())
+    # needle covariances with radii of hundreds of pixels are ill-conditioned in fp32 whoever computes them: the bound
+    # is a few times what the ORACLE's own fp32 instance differs from its fp64 instance on the same scene
+    st32 = gs_oracle.forward(rs, sc.means3D, sc.opacities, shs=sc.shs, scales=sc.scales, rotations=sc.rotations,
+                             dtype=np.float32)
+    ref32 = gs_oracle.backward(st32, w.numpy())
     for k in ("means3D", "opacities", "scales", "rotations"):
         r = getattr(ref, k)
         if np.abs(r).max() > 1e-6:
-            assert max_rel_err(grads[k].reshape(r.shape), r) < 2e-2, k      # edge-case scenes: threshold flips allowed
+            tol = max(2e-2, 6.0 * max_rel_err(getattr(ref32, k), r))
+            assert max_rel_err(grads[k].reshape(r.shape), r) < tol, (k, tol)
