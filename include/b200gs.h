@@ -325,6 +325,9 @@ int64_t b200gs_launch_count(int reset);
  *                 (must not change between a forward call and its backward call)
  *   "project":    0 (default) projection kernel with one thread per Gaussian; 1 dense-warp variant (warp-level
  *                 stream compaction: cull -> geometry -> colour)
+ *   "bwd_overlap": 0 (default) the projection adjoint writes every gradient row, zeros included; 1 the gradient
+ *                 tensors are zero-filled on an internal side stream while the compositing adjoint runs and the
+ *                 projection adjoint writes only the rows of visible Gaussians
  *   "sort":       0 CUB radix sort, 1 automatic (default: single-launch cooperative radix sort for
  *                 pair lists <= 256 k, CUB above), 2 cooperative sort whenever the list is <= 3 M
  * Environment equivalents read at first use: B200GS_BIN_SHIFT, B200GS_GATHER=tma|ldgsts,

@@ -161,6 +161,39 @@ static bool use_slab() {
   return m == 1;
 }
 
+// backward zero-fill: 1 = the gradient tensors are zero-filled with memsets on a side stream WHILE the compositing
+// adjoint runs (it is issue-bound and leaves HBM idle), and the projection adjoint then writes only the rows of
+// Gaussians that reached the image; 0 = the projection adjoint writes every row itself (one pass, no memset).
+// b200gs_set_option("bwd_overlap", 0|1), B200GS_BWD_OVERLAP=0|1.
+static std::atomic<int> g_bwd_overlap{-1};
+static bool use_bwd_overlap() {
+  int m = g_bwd_overlap.load();
+  if (m < 0) {
+    const char* e = getenv("B200GS_BWD_OVERLAP");
+    m = (e && atoi(e) == 1) ? 1 : 0;
+    g_bwd_overlap.store(m);
+  }
+  return m == 1;
+}
+struct SideStream { cudaStream_t side = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+static std::mutex g_side_mu;
+static std::vector<std::pair<std::pair<int, cudaStream_t>, SideStream>> g_sides;   // one per (device, caller stream)
+static SideStream* side_stream_for(cudaStream_t st) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(g_side_mu);
+  for (auto& e : g_sides) if (e.first.first == dev && e.first.second == st) return &e.second;
+  SideStream s;
+  if (cudaStreamCreateWithFlags(&s.side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  g_sides.push_back({{dev, st}, s});
+  return &g_sides.back().second;
+}
+
 // pair keys of the global sort: 32-bit (bin << 24 | quantised depth, exact order restored in the ranges
 // pass; default whenever there are at most 255 bins and the library sort is used) or 64-bit.
 // b200gs_set_option("sort_keys", 32|64), B200GS_SORT_KEYS=64.
@@ -324,6 +357,10 @@ int b200gs_set_option(const char* name, int value) {
   }
   if (name && !strcmp(name, "render")) {
     g_render_mode.store(value < 0 ? -1 : (value == 0 ? 0 : 1));
+    return 0;
+  }
+  if (name && !strcmp(name, "bwd_overlap")) {
+    g_bwd_overlap.store(value == 1 ? 1 : 0);
     return 0;
   }
   if (name && !strcmp(name, "project")) {
@@ -691,6 +728,25 @@ int b200gs_backward(const B200GSParams* prm, const float* bg, const float* viewm
   float* grad2d = reinterpret_cast<float*>(g2_p);
   if ((rc = check_cuda(cudaMemsetAsync(grad2d, 0, g2_bytes, st), "clear grad2d"))) return rc;
 
+  // fork: zero-fill of the outputs on a side stream, overlapped with the compositing adjoint
+  SideStream* side = (use_bwd_overlap() && num_rendered > 0) ? side_stream_for(st) : nullptr;
+  if (side) {
+    rc = check_cuda(cudaEventRecord(side->fork, st), "backward: fork");
+    if (!rc) rc = check_cuda(cudaStreamWaitEvent(side->side, side->fork, 0), "backward: fork wait");
+    auto zero = [&](void* p, size_t bytes) {
+      if (!rc && p && bytes) rc = check_cuda(cudaMemsetAsync(p, 0, bytes, side->side), "backward: zero-fill");
+    };
+    zero(dL_dmeans3D, sizeof(float) * 3 * (size_t)P);
+    zero(dL_dmeans2D, sizeof(float) * 3 * (size_t)P);
+    zero(dL_dopacities, sizeof(float) * (size_t)P);
+    if (shs) zero(dL_dshs, sizeof(float) * 3 * (size_t)prm->M * (size_t)P);
+    if (colors_precomp) zero(dL_dcolors_precomp, sizeof(float) * 3 * (size_t)P);
+    if (scales) { zero(dL_dscales, sizeof(float) * 3 * (size_t)P); zero(dL_drotations, sizeof(float) * 4 * (size_t)P); }
+    if (cov3D_precomp) zero(dL_dcov3D, sizeof(float) * 6 * (size_t)P);
+    if (!rc) rc = check_cuda(cudaEventRecord(side->join, side->side), "backward: join record");
+    if (rc) return rc;
+  }
+
   if (num_rendered > 0) {
     RenderBwdArgs ra;
     ra.W = W; ra.H = H; ra.gbx = gbx; ra.bin_shift = bs; ra.ranges = ib.ranges; ra.point_list = bb.vals_sorted;
@@ -705,8 +761,10 @@ int b200gs_backward(const B200GSParams* prm, const float* bg, const float* viewm
     if ((rc = debug_sync(prm, st, "render backward"))) return rc;
   }
 
+  if (side && (rc = check_cuda(cudaStreamWaitEvent(st, side->join, 0), "backward: join"))) return rc;
   ProjectBwdArgs pa;
   pa.P = P; pa.M = prm->M; pa.W = W; pa.H = H;
+  pa.active_only = side ? 1 : 0;
   static const bool no_slab = getenv("B200GS_NO_SLAB") != nullptr;     // read once per process
   pa.slab = no_slab ? -1 : 0;
   pa.sh_vec = (shs && (prm->M & 3) == 0 && (reinterpret_cast<uintptr_t>(shs) & 15) == 0 &&

@@ -119,6 +119,7 @@ struct RenderBwdArgs {
 struct ProjectBwdArgs {
   int P, M, W, H, sh_vec;
   int slab;   // in: -1 disables the shared-memory SH-gradient slab; set by the launcher
+  int active_only;   // outputs were zero-filled beforehand: write only the rows of Gaussians that reached the image
   float tanfovx, tanfovy, scale_modifier;
   const float *means, *scales, *rots, *shs, *cov3d_precomp;
   const float *view, *proj, *campos;

@@ -681,6 +681,9 @@ __global__ void __launch_bounds__(256, PROJECT_BWD_MIN_BLOCKS) k_project_bwd(Pro
   float g2x = 0.f, g2y = 0.f, gop = 0.f;
   float gcol[3] = {0.f, 0.f, 0.f};
   const bool active = in_range && a.radii[i] > 0 && a.tiles[i] != 0u;     // (tiles[] may hold a packed footprint)
+  // active_only: every gradient tensor was zero-filled beforehand (on a side stream, under the compositing adjoint);
+  // only the rows of Gaussians that reached the image are written here (the launcher disables the slab)
+  if (a.active_only && !active) return;
   const bool vec_ok = a.sh_vec != 0;
 
   if (active) {
@@ -1009,7 +1012,7 @@ void launch_project_bwd(const ProjectBwdArgs& a_in, int deg, cudaStream_t st) {
   // SH-gradient slab through shared memory + TMA bulk store: rows must be 16-byte multiples and the slab
   // must fit the default 48 KB of dynamic shared memory (M <= 16)
   const size_t slab_bytes = (size_t)256 * a.M * 12;
-  a.slab = (deg >= 0 && a.sh_vec && slab_bytes <= 48 * 1024 && a.slab >= 0) ? 1 : 0;
+  a.slab = (deg >= 0 && a.sh_vec && slab_bytes <= 48 * 1024 && a.slab >= 0 && !a.active_only) ? 1 : 0;
   const size_t sm = a.slab ? slab_bytes : 0;
   switch (deg) {
     case -1: k_project_bwd<-1><<<grid, block, 0, st>>>(a); break;

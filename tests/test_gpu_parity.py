@@ -647,3 +647,28 @@ def test_bin_count_limits_of_the_bucketed_binning(W, H, shift, expect_bucketed):
     st = _oracle(rs, sc, np.float32)
     assert psnr(color, st.color) >= PSNR_MIN
     assert (radii != st.radii).mean() <= 1e-3
+
+
+def test_backward_zero_fill_overlap_gives_the_same_gradients():
+    """Option "bwd_overlap": gradient tensors zero-filled on a side stream under the compositing adjoint, projection
+    adjoint writes only the rows of visible Gaussians -- every gradient element must equal the one-pass result
+    (culled Gaussians: exact zeros), for SH and precomputed-colour inputs."""
+    from robosimgs_b200 import _cabi
+    sc, cam, rs = small_scene(P=5003, degree=2, W=200, H=136, eye=(0.2, 0.1, 0.6), fov=65.0)
+    w = torch.rand(3, 136, 200, generator=torch.Generator().manual_seed(23))
+    cols = torch.rand(5003, 3, generator=torch.Generator().manual_seed(24))
+    try:
+        for kw in ({}, {"colors_precomp": cols}):
+            out = {}
+            for mode in (0, 1, 1):
+                _cabi.set_option("bwd_overlap", mode)
+                out[mode] = gpu_render(sc, cam, 2, bg=(0.2, 0.1, 0.4), grad_weight=w, **kw)
+            assert np.array_equal(out[0][0], out[1][0])
+            culled = out[0][1] <= 0
+            assert culled.mean() > 0.2
+            for k in out[0][2]:
+                a, b = out[0][2][k], out[1][2][k]
+                assert max_rel_err(b, a) < 1e-5, k
+                assert not np.any(b.reshape(5003, -1)[culled]), k          # exact zeros where nothing was rendered
+    finally:
+        _cabi.set_option("bwd_overlap", 0)
