@@ -157,6 +157,8 @@ def run_reference(args):
         "config": {"workload": WORKLOAD, "P": P_SCENE, "D_reference_rects": int(st.num_rendered),
                    "P_vis": int((st.radii > 0).sum())},
         "cpu_baseline": {"value": val, "unit": "Mpixels/s", "cores": gs_oracle.num_threads(), "kind": "port",
+                         "threads_per_stage": {"preprocess": gs_oracle.num_threads(), "bin_and_sort": 1,
+                                               "render": gs_oracle.num_threads()},
                          "sample": f"{args.steps} full 1920x1080 frames (preprocess + bin/sort + render), "
                                    "oracle/gs_oracle.c fp32, OpenMP"},
         "e2e": {"value": val, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -508,6 +510,9 @@ def run_b200(args):
             "value": n * px / dt / 1e6, "unit": "Mpixels/s", "cores": gs_oracle.num_threads(), "kind": "port",
             "sample": f"{n} full 1920x1080 frames of the same scene/camera (oracle/gs_oracle.c fp32, OpenMP)",
             "preprocess_only_ms": pre_s * 1e3, "D_reference_rects": int(st.num_rendered),
+            "threads_per_stage": {"preprocess": gs_oracle.num_threads(), "bin_and_sort": 1, "render": gs_oracle.num_threads()},
+            "note": "a checker, not a tuned CPU renderer: the binning/sort stage of the oracle is serial (17 M pairs, about "
+                    "1 s of the frame); the GPU/CPU ratio says nothing about kernel quality",
             "cpu_count": cores,
         }
         out["config"]["D_reference_rects"] = int(st.num_rendered)
