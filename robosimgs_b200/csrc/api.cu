@@ -256,7 +256,7 @@ static ImgBuf carve_img(char* base, int H, int W, size_t* bytes) {
   im.ranges = c.take<uint2>(tiles);
   im.pix = c.take<float4>((size_t)H * W);
   im.n_contrib = c.take<uint32_t>((size_t)H * W);
-  im.bin_pub = c.take<unsigned long long>(BUCKET_BINS_MAX);   // 8 KB: bucket_count follows without a gap
+  im.bin_pub = c.take<unsigned long long>(BUCKET_BINS_MAX);   // 512 KB: bucket_count follows without a gap
   im.bucket_count = c.take<uint32_t>(BUCKETS_MAX);
   im.bucket_base = c.take<uint32_t>(BUCKETS_MAX + 4);
   im.bucket_cursor = c.take<uint32_t>(BUCKETS_MAX);
@@ -465,8 +465,8 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
   pa.view = viewmatrix; pa.proj = projmatrix; pa.campos = campos;
   pa.radii = radii; pa.rec = gb.rec; pa.depth_key = gb.depth_key; pa.tiles = gb.tiles;
   pa.clamped = gb.clamped;
-  // bucketed binning: at most BUCKET_BINS_MAX bins (one scan CTA each, look-back over the lower bins)
-  const bool bucketed = use_bucketed() && (uint32_t)num_tiles <= BUCKET_BINS_MAX;
+  // bucketed binning: bin ids travel in 16 bits through the staged emission, and every bin needs >= 4 depth slices
+  const bool bucketed = use_bucketed() && (uint32_t)num_tiles < 65535u && (uint32_t)num_tiles * 4u <= BUCKETS_MAX;
   // depth slices per bin: as many as the bucket tables hold, but no more buckets than ~4 per Gaussian (a 10 k-Gaussian
   // scene must not clear and scan half a million counters)
   const uint32_t bucket_budget = (uint32_t)std::min<uint64_t>(BUCKETS_MAX, std::max<uint64_t>(4ull * (uint64_t)P, 4096ull));
@@ -485,10 +485,12 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
   pa.slice_shift = 27 - slices_log2;      // 16 octaves of depth from the near plane over 2^slices_log2 slices
   pa.near_bits = near_bits;
   pa.pack_tiles = (bucketed && num_tiles <= 255) ? 1 : 0;
-  // bucket counters and, directly in front of them, the look-back words of the bucket scan
+  // bucket counters and, directly in front of them, the look-back words of the bucket scan (the LAST num_tiles words
+  // of the table, so that one memset of minimal length clears both)
+  unsigned long long* const bin_pub = ib.bin_pub + (BUCKET_BINS_MAX - (uint32_t)(bucketed ? num_tiles : 0));
   if (bucketed && P > 0 &&
-      (rc = check_cuda(cudaMemsetAsync(ib.bin_pub, 0, sizeof(unsigned long long) * BUCKET_BINS_MAX +
-                                                        sizeof(uint32_t) * (size_t)num_buckets, st),
+      (rc = check_cuda(cudaMemsetAsync(bin_pub, 0, sizeof(unsigned long long) * (size_t)num_tiles +
+                                                     sizeof(uint32_t) * (size_t)num_buckets, st),
                        "clear bucket counters")))
     return rc;
   {
@@ -504,7 +506,7 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
   ba.num_bins = (uint32_t)num_tiles; ba.capacity = 0xFFFFFFFFu;
   ba.tiles = gb.tiles; ba.depth_key = gb.depth_key; ba.rec = gb.rec; ba.radii = radii;
   ba.bucket_count = ib.bucket_count; ba.bucket_base = ib.bucket_base; ba.bucket_cursor = ib.bucket_cursor;
-  ba.bin_pub = ib.bin_pub; ba.ranges = ib.ranges;
+  ba.bin_pub = bin_pub; ba.ranges = ib.ranges;
   ba.total = gb.counters + 1;
   ba.big_seg_count = gb.counters + 2; ba.total_windows = gb.counters + 3;
   ba.win_first = nullptr; ba.win_capacity = 0; ba.big_segs = nullptr;
@@ -543,7 +545,7 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
       // queue length of the large segments and window count; counters[1] = D is rewritten by the scan
       if ((rc2 = check_cuda(cudaMemsetAsync(gb.counters, 0, 4 * sizeof(uint32_t), st), "clear queue lengths"))) return rc2;
       if (!bin_pub_clean &&
-          (rc2 = check_cuda(cudaMemsetAsync(ib.bin_pub, 0, sizeof(unsigned long long) * (size_t)num_tiles, st),
+          (rc2 = check_cuda(cudaMemsetAsync(bin_pub, 0, sizeof(unsigned long long) * (size_t)num_tiles, st),
                             "clear look-back words")))
         return rc2;
       BucketArgs b2 = ba;
@@ -718,7 +720,8 @@ int b200gs_backward(const B200GSParams* prm, const float* bg, const float* viewm
   const int tile_bits = tile_bits_for(gbx * gby);
   GeomBuf gb = carve_geom(const_cast<char*>(geom), P, nullptr);
   // the record slab exists iff the forward call ran the bucketed binning with option "slab" and the four-pixel kernels
-  const bool slab = use_slab() && use_render4(gx * gy) && use_bucketed() && (uint32_t)(gbx * gby) <= BUCKET_BINS_MAX;
+  const bool slab = use_slab() && use_render4(gx * gy) && use_bucketed() && (uint32_t)(gbx * gby) < 65535u &&
+                    (uint32_t)(gbx * gby) * 4u <= BUCKETS_MAX;
   BinBuf bb = carve_binning(const_cast<char*>(binning), num_rendered, tile_bits, nullptr, slab);
   ImgBuf ib = carve_img(const_cast<char*>(img), H, W, nullptr);
 

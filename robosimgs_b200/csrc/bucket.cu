@@ -29,6 +29,8 @@
 //                    inside the segment, L2-resident ping-pong.
 //
 // Four launches behind the projection kernel, no scan over Gaussians, no padding of a speculative capacity, no ranges pass, no tie repair.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "spans.cuh"
@@ -37,10 +39,11 @@
 namespace b200gs {
 
 // ---- k_bucket_scan --------------------------------------------------------------------------------
-// One CTA per bin.  bin_pub[bin] = valid bit | windows << 32 | pairs, published once the bin's own scan is done;
-// a bin's offsets are the sums over the lower bins (CTAs are dispatched in index order, so a CTA only ever waits
-// for CTAs that are already running or done -- the usual decoupled look-back argument).
-constexpr int SCAN_THREADS = 1024;
+// One CTA per bin.  A bin's offsets are the sums over the lower bins, obtained by a decoupled look-back over the words
+// the bins publish in bin_pub[] (CTAs are dispatched in index order, so a CTA only ever waits for CTAs that are
+// already running or done).
+constexpr int SCAN_THREADS = 1024;     // launched with min(1024, max(32, S / 4)) threads: four counters per thread
+                                       // (eight at 8192 slices)
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_bucket_scan(BucketArgs a) {
   __shared__ uint32_t s_warp[32];
@@ -74,7 +77,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_bucket_scan(BucketArgs a) {
   if (lane == 31) s_warp[warp] = incl;
   __syncthreads();
   if (warp == 0) {
-    const uint32_t w = s_warp[lane];
+    const uint32_t w = lane < (blockDim.x >> 5) ? s_warp[lane] : 0u;
     uint32_t wi = w;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -84,21 +87,32 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_bucket_scan(BucketArgs a) {
     s_warp[lane] = wi - w;                                   // exclusive prefix of the warp totals
     const uint32_t bin_total = __shfl_sync(0xffffffffu, wi, 31);
     const uint32_t nwin = (bin_total + BUCKET_WINDOW - 1) / BUCKET_WINDOW;
+    // Decoupled look-back.  A bin first publishes its own AGGREGATE (pairs, windows), then -- once it knows the sums
+    // over all lower bins -- its INCLUSIVE PREFIX; a bin looks back 32 words at a time until it meets a prefix, so the
+    // walk is a few words long whatever the number of bins.  Word: status (2 bits) | windows (30) | pairs (32).
     volatile unsigned long long* pub = reinterpret_cast<volatile unsigned long long*>(a.bin_pub);
-    if (lane == 0) pub[bin] = (1ull << 63) | ((unsigned long long)nwin << 32) | bin_total;
-    // look-back over the lower bins
+    constexpr unsigned long long ST_AGG = 1ull << 62, ST_PREFIX = 2ull << 62;
+    if (lane == 0) pub[bin] = ST_AGG | ((unsigned long long)nwin << 32) | bin_total;
     uint32_t off = 0, woff = 0;
-    for (uint32_t j = lane; j < bin; j += 32) {
-      unsigned long long v;
-      do { v = pub[j]; } while (!(v >> 63));
-      off += (uint32_t)v;
-      woff += (uint32_t)(v >> 32) & 0x7FFFFFFFu;
+    for (int64_t hi = (int64_t)bin - 1; hi >= 0; hi -= 32) {
+      const int64_t j = hi - lane;
+      unsigned long long v = ST_PREFIX;                     // lanes past bin 0 contribute an empty prefix
+      if (j >= 0) do { v = pub[j]; } while (!(v >> 62));
+      // the nearest prefix (smallest lane) ends the walk: lanes nearer than it add their aggregates, it adds itself
+      const uint32_t is_prefix = __ballot_sync(0xffffffffu, (v >> 62) == 2ull);
+      const int first = is_prefix ? __ffs(is_prefix) - 1 : 32;
+      if (lane <= first && j >= 0) {
+        off += (uint32_t)v;
+        woff += (uint32_t)(v >> 32) & 0x3FFFFFFFu;
+      }
+      if (is_prefix) break;
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
       off += __shfl_xor_sync(0xffffffffu, off, d);
       woff += __shfl_xor_sync(0xffffffffu, woff, d);
     }
+    if (lane == 0) pub[bin] = ST_PREFIX | ((unsigned long long)(woff + nwin) << 32) | (unsigned long long)(off + bin_total);
     if (lane == 0) { s_off[0] = off; s_off[1] = woff; s_off[2] = bin_total; }
   }
   __syncthreads();
@@ -471,7 +485,8 @@ __global__ void __launch_bounds__(BS_THREADS) k_bucket_sort_big(BucketArgs a) {
 
 // ---- host ---------------------------------------------------------------------------------------
 void launch_bucket_scan(const BucketArgs& a, cudaStream_t st) {
-  k_bucket_scan<<<a.num_bins, SCAN_THREADS, 0, st>>>(a);
+  const int threads = std::min(SCAN_THREADS, std::max(32, (1 << a.slices_log2) / 4));
+  k_bucket_scan<<<a.num_bins, threads, 0, st>>>(a);
   count_launch();
 }
 

@@ -4,9 +4,10 @@
 
 namespace b200gs {
 
-// bucketed binning (bucket.cu): (bin, depth slice) buckets, at most BUCKET_BINS_MAX bins of 4..8192 slices
+// bucketed binning (bucket.cu): (bin, depth slice) buckets, at most BUCKET_BINS_MAX bins of 4..8192 slices each
 constexpr uint32_t BUCKETS_MAX = 512 * 1024;
-constexpr uint32_t BUCKET_BINS_MAX = 1024;
+constexpr uint32_t BUCKET_BINS_MAX = 65536;   // table size; bin ids travel in 16 bits through the staged emission, so
+                                              // the bucketed path serves images of up to 65534 bins
 constexpr int BUCKET_SLICES_LOG2_MAX = 13;
 constexpr uint32_t BUCKET_WINDOW = 192;   // pairs per sorter warp (cut at the next bucket boundary)
 

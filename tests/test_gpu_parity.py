@@ -622,17 +622,18 @@ def test_dense_warp_projection_kernels_are_bit_identical(degree, precomp):
         _cabi.set_option("binning", -1)
 
 
-@pytest.mark.parametrize("W,H,shift,expect_bucketed", [(512, 512, 0, True), (1104, 1104, 0, False), (1920, 1080, 1, False),
-                                                       (1920, 1080, 2, True)])
+@pytest.mark.parametrize("W,H,shift,expect_bucketed", [(512, 512, 0, True), (1104, 1104, 0, True), (1920, 1080, 0, True),
+                                                       (1920, 1080, 2, True), (4096, 4096, 0, False)])
 def test_bin_count_limits_of_the_bucketed_binning(W, H, shift, expect_bucketed):
-    """The bucket scan runs one CTA per bin with a look-back over the lower bins and is used up to 1024 bins
-    (512 slices each at the limit); images with more bins take the library-sort pipeline.  Both sides of the limit
-    against the oracle, and the many-bin look-back (1024 CTAs) against the few-bin one, bit for bit."""
+    """The bucket scan runs one CTA per bin with a decoupled look-back (aggregate / inclusive-prefix words) over the
+    lower bins; it serves up to 65534 bins (bin ids travel in 16 bits), images with more bins take the library-sort
+    pipeline.  Few bins with thousands of slices, thousands of bins with a handful of slices each (8160 scan CTAs at
+    1080p with 16-px bins), and the far side of the limit: against the oracle, and bit for bit against 128-px bins."""
     from robosimgs_b200 import _cabi
     from robosimgs_b200.cameras import camera_look_at
     from robosimgs_b200.scenes import cube_scene, settings_from_camera
     bins = -(-((W + 15) // 16) // (1 << shift)) * -(-((H + 15) // 16) // (1 << shift))
-    assert (bins <= 1024) == expect_bucketed
+    assert (bins < 65535 and bins * 4 <= 512 * 1024) == expect_bucketed
     sc, _ = cube_scene(P=20000, seed=9, degree=1)
     cam = camera_look_at((0.4, 0.3, 3.2), (0, 0, 0), (0, 1, 0), 55.0, W, H)
     rs = settings_from_camera(cam, 1, bg=(0.1, 0.2, 0.3))
