@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <deque>
 #include <atomic>
 #include <functional>
 #include <mutex>
@@ -177,7 +178,8 @@ static bool use_bwd_overlap() {
 }
 struct SideStream { cudaStream_t side = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
 static std::mutex g_side_mu;
-static std::vector<std::pair<std::pair<int, cudaStream_t>, SideStream>> g_sides;   // one per (device, caller stream)
+static std::deque<std::pair<std::pair<int, cudaStream_t>, SideStream>> g_sides;   // one per (device, caller stream);
+                                                                                 // deque: entries never move
 static SideStream* side_stream_for(cudaStream_t st) {
   int dev = 0;
   cudaGetDevice(&dev);
