@@ -356,7 +356,8 @@ def run_b200(args):
     # ---- e2e: HOST buffers on both sides through the public per-frame renderer (sweep.SceneRenderer):
     # camera block from pinned host memory in, finished 8-bit frame in pinned host memory out, every
     # frame collected (and its pair-count ticket validated) by the consumer inside the timed region ----
-    NS = max(1, args.e2e_streams)
+    from robosimgs_b200.sweep import host_frames_in_flight
+    NS = args.e2e_streams if args.e2e_streams > 0 else host_frames_in_flight(int(os.environ.get("LOCAL_WORLD_SIZE", world)))
     renderer = SceneRenderer(tens, SH_DEG, bg, H_IMG, W_IMG, streams=NS, graphs=not args.no_graphs)
     h2d_bytes = 35 * 4
     d2h_bytes = H_IMG * W_IMG * 3
@@ -584,8 +585,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-grad", action="store_true", help="skip the fp64 oracle gradient check of the parity block")
     ap.add_argument("--streams", type=int, default=4, help="CUDA streams the frames of the sweep alternate over")
-    ap.add_argument("--e2e-streams", type=int, default=6,
-                    help="same, for the end-to-end (host buffers) measurement (measured: 0.234 ms/frame at 4, 0.188 at 6 and 8)")
+    ap.add_argument("--e2e-streams", type=int, default=0,
+                    help="same, for the end-to-end (host buffers) measurement; 0 = sweep.host_frames_in_flight "
+                         "(6 for one or two ranks on the box, 4 from four ranks up where the host path is the bound)")
     ap.add_argument("--no-graphs", action="store_true", help="end-to-end path without CUDA graphs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

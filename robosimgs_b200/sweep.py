@@ -83,6 +83,16 @@ def bind_rank_to_cores(local_rank: int, local_world: int):
     return mine
 
 
+def host_frames_in_flight(local_world: int) -> int:
+    """Frames in flight per GPU for the host-buffer path (SceneRenderer with host_frames=True).
+    One rank alone on the box is bound by its kernels and by the launch latency of the short binning kernels: six
+    frames in flight hide them (C3: 0.234 ms/frame at 4, 0.188 at 6 and 8).  With four or more ranks the box's
+    device->host path is the bound: more frames in flight only add concurrent copies to a saturated
+    path -- on 8 GPUs six instead of four cost 4 % on C3 (32.7 -> 31.3 Gpixel/s) and 40 % on the short C4 sweep
+    (12.4 k -> 7.3 k frames/s, profiles/r2_c4_sweep_n8_streams6.json)."""
+    return 6 if local_world <= 2 else 4
+
+
 class FrameStreams:
     """Round-robin CUDA streams for INDEPENDENT frames of a sweep.
 
@@ -334,7 +344,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cameras", type=int, default=64)
     ap.add_argument("--gaussians", type=int, default=3_000_000)
-    ap.add_argument("--streams", type=int, default=6)
+    ap.add_argument("--streams", type=int, default=0, help="frames in flight per GPU (0: host_frames_in_flight)")
     ap.add_argument("--repeat", type=int, default=4, help="passes over this rank's cameras inside the timed region")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -342,7 +352,10 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    bind_rank_to_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+    bind_rank_to_cores(local, local_world)
+    if a.streams <= 0:
+        a.streams = host_frames_in_flight(local_world)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)

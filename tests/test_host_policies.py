@@ -75,3 +75,10 @@ def test_scene_renderer_capacity_never_shrinks_on_overflow():
     assert r.capacity == c5
     r._set_capacity(0)
     assert r.capacity == 0
+
+
+def test_frames_in_flight_follow_the_ranks_on_the_box():
+    # one or two ranks are kernel/launch bound (six frames hide the binning latency); from four ranks up the
+    # device->host path of the box is the bound and more frames in flight only add concurrent copies
+    from robosimgs_b200.sweep import host_frames_in_flight
+    assert [host_frames_in_flight(n) for n in (1, 2, 4, 8)] == [6, 6, 4, 4]
