@@ -79,74 +79,78 @@ __global__ void __launch_bounds__(R4_THREADS, R4_FWD_MINB) k_render_fwd4(RenderA
 
   ring.prologue();
 
-  // A finished pixel (transmittance test failed once, or outside the image) is marked by a NEGATIVE
-  // transmittance: |T| stays the final transmittance, T * (1 - alpha) can never pass the 1e-4 test
-  // again, so the hot loop needs no separate flag.  nstop = list position of the record that
-  // finished the pixel (n if none did): nothing at or behind it contributes, and every record in
-  // front of it that the adjoint finds valid did contribute -- all the adjoint needs to know.
-  // Pixel state lives in register PAIRS (pixels 0|1 and 2|3): everything up to the three tests below is issued
-  // as packed f32x2 instructions (FADD2 / FFMA2 / FMUL2, sm_100) -- one issue slot for two pixels.  Every packed
+  // A finished pixel (transmittance test failed once, or outside the image) is marked by an INFINITE x coordinate:
+  // for every later record ndx = +inf, power2 = fma(inf, fma(-hA, inf, bdy), -cdy2) = -inf (hA > 0 for unmarked
+  // records; marked ones skip a NaN/+inf power explicitly), so its alpha is exactly 0 and the record acts on the
+  // pixel as the identity -- T keeps the final transmittance, the hot loop needs no flag and no predicate for it.
+  // nstop = list position of the record that finished the pixel (n if none did): nothing at or behind it
+  // contributes, and every record in front of it that the adjoint finds valid did contribute -- all the adjoint
+  // needs to know.
+  // Pixel state lives in register PAIRS (pixels 0|1 and 2|3) and the whole evaluation is issued as packed f32x2
+  // instructions (FADD2 / FFMA2 / FMUL2, sm_100) -- one issue slot for two pixels.  Every packed
   // operation rounds exactly like the scalar expression it replaces (and like render.cu's one-pixel kernels):
   //   ndx = px - x (= -dx);  power2 = fma(ndx, fma(-hA, ndx, bdy), -cdy2);  1 - alpha = fma(alpha, -1, 1).
+  const float FIN = __int_as_float(0x7f800000);
   float2 T[2], Cr[2], Cg[2], Cb[2], pxf2[2];
   uint32_t nstop[4];
 #pragma unroll
   for (int h = 0; h < 2; h++) {
-    T[h] = make_float2(t.in[2 * h] ? 1.f : -1.f, t.in[2 * h + 1] ? 1.f : -1.f);
+    T[h] = make_float2(1.f, 1.f);
     Cr[h] = Cg[h] = Cb[h] = make_float2(0.f, 0.f);
-    pxf2[h] = make_float2(t.pxf[2 * h], t.pxf[2 * h + 1]);
+    pxf2[h] = make_float2(t.in[2 * h] ? t.pxf[2 * h] : FIN, t.in[2 * h + 1] ? t.pxf[2 * h + 1] : FIN);
     nstop[2 * h] = n; nstop[2 * h + 1] = n;
   }
 
-  // One record against the thread's four pixels.  CLAMP = false for unmarked records (opacity <= 0.99 and a safely
-  // positive definite conic): then power <= 0 for every pixel, G <= 1 and min(0.99, o*G) is the identity.
-  // The accumulate is predicated, not selected: FSETP/FSEL/FMNMX share the half-rate ALU pipe, which
-  // co-limits this loop with the issue rate (ncu: math-pipe throttle).
+  // One record against the thread's four pixels.  A pixel the record does not reach (alpha < 1/255; for marked
+  // records also power > 0) takes alpha = 0: w = 0, C + c*0 = C and T*(1 - 0) = T are exact, so the accumulate is
+  // unconditional and packed.  The only data-dependent control flow is the once-per-pixel "transmittance exhausted"
+  // event (T*(1 - alpha) < 1e-4 with T >= 1e-4 needs alpha > 0.99 * ... i.e. a record that does reach the pixel):
+  // then the record is applied pixel by pixel and the exhausted ones are retired.
   // GENERAL = the record is marked (negative radius, project.cu:record_is_general): clamp alpha at 0.99 and skip
   // pixels whose power rounds above 0.  Unmarked records can do neither, so both tests are dropped for them.
-  auto eval = [&](const float4& q0, const float4& q1, const float4& q2, uint32_t pos, auto clamp_tag) {
+  float pyf = t.pyf;
+  asm volatile("" : "+f"(pyf));   // keep the row coordinate in its register (ptxas would re-derive it per record)
+  auto eval = [&](const float4& q0, const float4& q1, const float4& q2, uint32_t c, uint32_t jj, auto clamp_tag) {
     constexpr bool CLAMP = decltype(clamp_tag)::value;
-    const RowTerms rt = row_terms(q0.z, q0.w, q1.x, q0.y - t.pyf);
+    const RowTerms rt = row_terms(q0.z, q0.w, q1.x, q0.y - pyf);
     const float2 nx2 = make_float2(-q0.x, -q0.x), nhA2 = make_float2(-rt.hA, -rt.hA);
     const float2 bdy2 = make_float2(rt.bdy, rt.bdy), ncdy2 = make_float2(-rt.cdy2, -rt.cdy2);
     const float2 o2 = make_float2(q1.y, q1.y);
-    bool stop[4];
+    float2 alpha[2], one_m[2];
 #pragma unroll
     for (int h = 0; h < 2; h++) {
       const float2 ndx = __fadd2_rn(pxf2[h], nx2);
       const float2 p2 = __ffma2_rn(ndx, __ffma2_rn(nhA2, ndx, bdy2), ncdy2);
-      float2 alpha = __fmul2_rn(o2, make_float2(ex2_fast(p2.x), ex2_fast(p2.y)));
-      if (CLAMP) alpha = make_float2(fminf(0.99f, alpha.x), fminf(0.99f, alpha.y));
-      const float2 test_T = __fmul2_rn(T[h], __ffma2_rn(alpha, make_float2(-1.f, -1.f), make_float2(1.f, 1.f)));
-      const bool valid0 = (!CLAMP || p2.x <= 0.f) && alpha.x >= (1.f / 255.f);
-      const bool valid1 = (!CLAMP || p2.y <= 0.f) && alpha.y >= (1.f / 255.f);
-      const bool upd0 = valid0 && test_T.x >= 0.0001f, upd1 = valid1 && test_T.y >= 0.0001f;
-      stop[2 * h] = valid0 && !(test_T.x >= 0.0001f);
-      stop[2 * h + 1] = valid1 && !(test_T.y >= 0.0001f);
-      if (upd0) {
-        const float w = alpha.x * T[h].x;
-        Cr[h].x = __fmaf_rn(q2.x, w, Cr[h].x);
-        Cg[h].x = __fmaf_rn(q2.y, w, Cg[h].x);
-        Cb[h].x = __fmaf_rn(q2.z, w, Cb[h].x);
-        T[h].x = test_T.x;
-      }
-      if (upd1) {
-        const float w = alpha.y * T[h].y;
-        Cr[h].y = __fmaf_rn(q2.x, w, Cr[h].y);
-        Cg[h].y = __fmaf_rn(q2.y, w, Cg[h].y);
-        Cb[h].y = __fmaf_rn(q2.z, w, Cb[h].y);
-        T[h].y = test_T.y;
+      float2 al = __fmul2_rn(o2, make_float2(ex2_fast(p2.x), ex2_fast(p2.y)));
+      if (CLAMP) al = make_float2(fminf(0.99f, al.x), fminf(0.99f, al.y));
+      const bool valid0 = (!CLAMP || p2.x <= 0.f) && al.x >= (1.f / 255.f);
+      const bool valid1 = (!CLAMP || p2.y <= 0.f) && al.y >= (1.f / 255.f);
+      alpha[h] = make_float2(valid0 ? al.x : 0.f, valid1 ? al.y : 0.f);
+      one_m[h] = __ffma2_rn(alpha[h], make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
+    }
+    {
+      const float2 t0 = __fmul2_rn(T[0], one_m[0]), t1 = __fmul2_rn(T[1], one_m[1]);
+      if (fminf(fminf(t0.x, t0.y), fminf(t1.x, t1.y)) < 0.0001f) {
+        // a pixel's transmittance is exhausted by this record (at most once per pixel): the record does not act on
+        // it (alpha := 0, the identity) and the pixel is retired
+        const uint32_t pos = c * R4_CH + jj;
+        if (t0.x < 0.0001f) { alpha[0].x = 0.f; one_m[0].x = 1.f; nstop[0] = pos; pxf2[0].x = FIN; }
+        if (t0.y < 0.0001f) { alpha[0].y = 0.f; one_m[0].y = 1.f; nstop[1] = pos; pxf2[0].y = FIN; }
+        if (t1.x < 0.0001f) { alpha[1].x = 0.f; one_m[1].x = 1.f; nstop[2] = pos; pxf2[1].x = FIN; }
+        if (t1.y < 0.0001f) { alpha[1].y = 0.f; one_m[1].y = 1.f; nstop[3] = pos; pxf2[1].y = FIN; }
       }
     }
-    if (stop[0] || stop[1] || stop[2] || stop[3]) {   // rare: at most once per pixel
+    const float2 cr2 = make_float2(q2.x, q2.x), cg2 = make_float2(q2.y, q2.y), cb2 = make_float2(q2.z, q2.z);
 #pragma unroll
-      for (int h = 0; h < 2; h++) {
-        if (stop[2 * h] && T[h].x > 0.f) { T[h].x = -T[h].x; nstop[2 * h] = pos; }
-        if (stop[2 * h + 1] && T[h].y > 0.f) { T[h].y = -T[h].y; nstop[2 * h + 1] = pos; }
-      }
+    for (int h = 0; h < 2; h++) {
+      const float2 w = __fmul2_rn(alpha[h], T[h]);
+      Cr[h] = __ffma2_rn(cr2, w, Cr[h]);
+      Cg[h] = __ffma2_rn(cg2, w, Cg[h]);
+      Cb[h] = __ffma2_rn(cb2, w, Cb[h]);
+      T[h] = __fmul2_rn(T[h], one_m[h]);
     }
   };
-  auto all_done = [&]() { return fmaxf(fmaxf(T[0].x, T[0].y), fmaxf(T[1].x, T[1].y)) < 0.f; };
+  auto all_done = [&]() { return fminf(fminf(pxf2[0].x, pxf2[0].y), fminf(pxf2[1].x, pxf2[1].y)) == FIN; };
 
   uint32_t c = 0;
   bool early = false;
@@ -173,9 +177,8 @@ __global__ void __launch_bounds__(R4_THREADS, R4_FWD_MINB) k_render_fwd4(RenderA
         mask &= mask - 1;
         const uint32_t jj = base + b;
         const float4 q0 = st[jj * REC_F4], q1 = st[jj * REC_F4 + 1], q2 = st[jj * REC_F4 + 2];
-        const uint32_t pos = c * R4_CH + jj;
-        if (q2.w < 0.f) eval(q0, q1, q2, pos, std::true_type{});
-        else eval(q0, q1, q2, pos, std::false_type{});
+        if (q2.w < 0.f) eval(q0, q1, q2, c, jj, std::true_type{});
+        else eval(q0, q1, q2, c, jj, std::false_type{});
       }
     }
     const int num_done = __syncthreads_count(all_done());
@@ -190,7 +193,7 @@ __global__ void __launch_bounds__(R4_THREADS, R4_FWD_MINB) k_render_fwd4(RenderA
   }
   ring.drain();
 
-  const float Tf[4] = {fabsf(T[0].x), fabsf(T[0].y), fabsf(T[1].x), fabsf(T[1].y)};
+  const float Tf[4] = {T[0].x, T[0].y, T[1].x, T[1].y};
   const float R_[4] = {Cr[0].x, Cr[0].y, Cr[1].x, Cr[1].y};
   const float G_[4] = {Cg[0].x, Cg[0].y, Cg[1].x, Cg[1].y};
   const float B_[4] = {Cb[0].x, Cb[0].y, Cb[1].x, Cb[1].y};
