@@ -108,6 +108,11 @@ __global__ void __launch_bounds__(R4_THREADS, R4_FWD_MINB) k_render_fwd4(RenderA
   // then the record is applied pixel by pixel and the exhausted ones are retired.
   // GENERAL = the record is marked (negative radius, project.cu:record_is_general): clamp alpha at 0.99 and skip
   // pixels whose power rounds above 0.  Unmarked records can do neither, so both tests are dropped for them.
+  // every pixel of this thread is retired (or outside the image): only changes where a pixel retires, so the warp can
+  // leave its list behind the very record that exhausted its last pixel for the price of one vote per record --
+  // at batch granularity (32 list positions) half a batch of evaluations per tile was spent on retired pixels
+  auto all_done = [&]() { return fminf(fminf(pxf2[0].x, pxf2[0].y), fminf(pxf2[1].x, pxf2[1].y)) == FIN; };
+  bool mine_done = all_done();
   float pyf = t.pyf;
   asm volatile("" : "+f"(pyf));   // keep the row coordinate in its register (ptxas would re-derive it per record)
   auto eval = [&](const float4& q0, const float4& q1, const float4& q2, uint32_t c, uint32_t jj, auto clamp_tag) {
@@ -138,6 +143,7 @@ __global__ void __launch_bounds__(R4_THREADS, R4_FWD_MINB) k_render_fwd4(RenderA
         if (t0.y < 0.0001f) { alpha[0].y = 0.f; one_m[0].y = 1.f; nstop[1] = pos; pxf2[0].y = FIN; }
         if (t1.x < 0.0001f) { alpha[1].x = 0.f; one_m[1].x = 1.f; nstop[2] = pos; pxf2[1].x = FIN; }
         if (t1.y < 0.0001f) { alpha[1].y = 0.f; one_m[1].y = 1.f; nstop[3] = pos; pxf2[1].y = FIN; }
+        mine_done = all_done();
       }
     }
     const float2 cr2 = make_float2(q2.x, q2.x), cg2 = make_float2(q2.y, q2.y), cb2 = make_float2(q2.z, q2.z);
@@ -150,7 +156,6 @@ __global__ void __launch_bounds__(R4_THREADS, R4_FWD_MINB) k_render_fwd4(RenderA
       T[h] = __fmul2_rn(T[h], one_m[h]);
     }
   };
-  auto all_done = [&]() { return fminf(fminf(pxf2[0].x, pxf2[0].y), fminf(pxf2[1].x, pxf2[1].y)) == FIN; };
 
   uint32_t c = 0;
   bool early = false;
@@ -161,7 +166,7 @@ __global__ void __launch_bounds__(R4_THREADS, R4_FWD_MINB) k_render_fwd4(RenderA
     __syncthreads();
     const float4* st = sm[c % R4_STAGES];
     for (uint32_t base = 0; base < cnt; base += 32) {
-      if (__all_sync(0xffffffffu, all_done())) break;
+      if (__all_sync(0xffffffffu, mine_done)) break;
       const uint32_t j = base + lane;
       bool hit = false;
       if (j < cnt) {
@@ -179,9 +184,10 @@ __global__ void __launch_bounds__(R4_THREADS, R4_FWD_MINB) k_render_fwd4(RenderA
         const float4 q0 = st[jj * REC_F4], q1 = st[jj * REC_F4 + 1], q2 = st[jj * REC_F4 + 2];
         if (q2.w < 0.f) eval(q0, q1, q2, c, jj, std::true_type{});
         else eval(q0, q1, q2, c, jj, std::false_type{});
+        if (__all_sync(0xffffffffu, mine_done)) break;
       }
     }
-    const int num_done = __syncthreads_count(all_done());
+    const int num_done = __syncthreads_count(mine_done);
     if (num_done == R4_THREADS) { early = true; break; }
     ring.refill(c);
   }
@@ -326,7 +332,9 @@ __global__ void __launch_bounds__(R4_THREADS, R4_BWD_MINB) k_render_bwd4(RenderB
       pxf2[h] = make_float2(t.pxf[2 * h], t.pxf[2 * h + 1]);
     }
   }
-  const uint32_t ncmax = max(max(nc[0], nc[1]), max(nc[2], nc[3]));
+  // nothing at or behind list position max(n_contrib) over the WARP's 128 pixels reaches any of them: those records
+  // are not even tested (at batch granularity half a batch of alpha evaluations per tile was spent behind it)
+  const uint32_t ncmax = __reduce_max_sync(0xffffffffu, max(max(nc[0], nc[1]), max(nc[2], nc[3])));
 
   uint32_t c = 0;
   bool early = false;
@@ -337,10 +345,10 @@ __global__ void __launch_bounds__(R4_THREADS, R4_BWD_MINB) k_render_bwd4(RenderB
     __syncthreads();
     const float4* st = sm[c % R4_STAGES];
     for (uint32_t base = 0; base < cnt; base += 32) {
-      if (__all_sync(0xffffffffu, c * R4_CH + base >= ncmax)) break;
+      if (c * R4_CH + base >= ncmax) break;
       const uint32_t j = base + lane;
       bool hit = false;
-      if (j < cnt) {
+      if (j < cnt && c * R4_CH + j < ncmax) {
         const float4 q0 = st[j * REC_F4], q1 = st[j * REC_F4 + 1];
         hit = r4_block_may_contribute_scaled(q0.x, q0.y, q0.z, q0.w, q1.x, q1.z, t.rx0, t.ry0, t.rx1, t.ry1);
         if (coarse && hit)
