@@ -179,6 +179,9 @@ __global__ void __launch_bounds__(32 * EMIT_WARPS) k_emit_bucket(BucketArgs a) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t tword = (r < a.P) ? a.tiles[r] : 0u;     // count, or a packed footprint of up to three bins
+  // the depth travels with the footprint word (one coalesced line each): loading it only once the footprint is known
+  // to be non-empty would put a second dependent round trip in front of the cursor atomics
+  const uint32_t dkey = (r < a.P) ? a.depth_key[r] : 0u;
   uint32_t n = tiles_count(tword);
   const uint32_t big_lanes = __ballot_sync(0xffffffffu, n > BUCKET_BIG_THRESHOLD);
   if (n > BUCKET_BIG_THRESHOLD) n = 0;          // large footprints: emitted by the whole warp below
@@ -193,11 +196,11 @@ __global__ void __launch_bounds__(32 * EMIT_WARPS) k_emit_bucket(BucketArgs a) {
   uint32_t rel = 0;
   if (n && (tword & TILES_PACKED)) {
     // small footprint: the projection kernel left the bin ids in tiles[] -- no record load, no span arithmetic
-    rel = rel_depth(a, a.depth_key[r]);
+    rel = rel_depth(a, dkey);
     uint32_t o = incl - n;
     for (uint32_t k = 0; k < n; k++, o++) stage[warp][o] = ((tword >> (8u * k)) & 0xFFu) | ((uint32_t)lane << 16);
   } else if (n) {
-    rel = rel_depth(a, a.depth_key[r]);
+    rel = rel_depth(a, dkey);
     const float4 q0 = a.rec[(size_t)r * REC_F4], q1 = a.rec[(size_t)r * REC_F4 + 1];
     const TileRect rect = bin_rect(reference_rect(q0.x, q0.y, a.radii[r], a.gx, a.gy), a.bin_shift);
     SpanCtx s;

@@ -5,6 +5,7 @@
 // a11 preprocessCUDA bwd, a12 checkFrustum -- of the public diff-gaussian-rasterization named by
 // BASELINE.json:north_star (third-party; the reference repo only delegates, README.md:75).
 // Arithmetic follows oracle/gs_oracle_impl.h step by step.
+#include <algorithm>
 #include <atomic>
 #include <cstdlib>
 
@@ -16,7 +17,10 @@
 namespace b200gs {
 
 #ifndef PROJECT_MIN_BLOCKS
-#define PROJECT_MIN_BLOCKS 4
+#define PROJECT_MIN_BLOCKS 3
+#endif
+#ifndef PROJECT_WAVES
+#define PROJECT_WAVES 2
 #endif
 #ifndef PROJECT_BWD_MIN_BLOCKS
 #define PROJECT_BWD_MIN_BLOCKS 3
@@ -170,17 +174,64 @@ __device__ __forceinline__ void load_sh_row(const float* __restrict__ row, bool 
 // ==================================================================================================
 // K1: projection + SH colour.  One thread per Gaussian.  DEG = -1: colours are precomputed.
 // ==================================================================================================
+// The Gaussian's dense parameters (44 bytes) are fetched one grid stride AHEAD of their use: k_project is a grid-stride
+// loop whose threads start the copy of their next Gaussian into a private shared-memory slot (LDGSTS, no register
+// holds the data in flight) before they work on the current one, so the two dependent DRAM round trips in front of
+// the geometry (means -> near-plane test -> scales / rotation / opacity) leave the critical path.  Scales, rotation
+// and opacity of a Gaussian behind the near plane are fetched for nothing -- they share 32-byte sectors with their
+// neighbours, the DRAM traffic is the same.   Slot: {mu.xyz, opacity} {s.xyz, -} {q}.
+struct ProjIn {
+  float3 mu, s;
+  float4 q;
+  float o;
+};
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void fetch_proj_in(const ProjectArgs& a, int i, float4* slot) {
+  float* f = reinterpret_cast<float*>(slot);
+  const float* m = a.means + 3 * (size_t)i;
+  cp_async4(f + 0, m); cp_async4(f + 1, m + 1); cp_async4(f + 2, m + 2);
+  cp_async4(f + 3, a.opac + i);
+  if (!a.cov3d_precomp) {
+    const float* sc = a.scales + 3 * (size_t)i;
+    cp_async4(f + 4, sc); cp_async4(f + 5, sc + 1); cp_async4(f + 6, sc + 2);
+    cp_async16(slot + 2, reinterpret_cast<const float4*>(a.rots) + i);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ ProjIn read_proj_in(const float4* slot) {
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  const float4 v0 = slot[0], v1 = slot[1], v2 = slot[2];
+  ProjIn in;
+  in.mu = make_float3(v0.x, v0.y, v0.z);
+  in.o = v0.w;
+  in.s = make_float3(v1.x, v1.y, v1.z);
+  in.q = v2;
+  return in;
+}
+
 template <int DEG>
 __global__ void __launch_bounds__(256, PROJECT_MIN_BLOCKS) k_project(ProjectArgs a) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ __align__(16) float4 s_in[256][3];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.P) return;
+  float4* const slot = s_in[threadIdx.x];
+  fetch_proj_in(a, i, slot);
   CamConst c;
   load_cam(c, a.view, a.proj, a.campos);
+  const int stride = gridDim.x * blockDim.x;
+  for (; i < a.P; i += stride) {
+  const ProjIn cur = read_proj_in(slot);
+  if (i + stride < a.P) fetch_proj_in(a, i + stride, slot);
 
   uint32_t key = 0xFFFFFFFFu, ntiles = 0, tiles_word = 0;
   int radius = 0;
 
-  const float3 mu = make_float3(__ldg(a.means + 3 * i), __ldg(a.means + 3 * i + 1), __ldg(a.means + 3 * i + 2));
+  const float3 mu = cur.mu;
   const float vz = c.v[2] * mu.x + c.v[6] * mu.y + c.v[10] * mu.z + c.v[14];
   if (vz > a.near_plane) {
     const float hx = c.p[0] * mu.x + c.p[4] * mu.y + c.p[8] * mu.z + c.p[12];
@@ -190,14 +241,12 @@ __global__ void __launch_bounds__(256, PROJECT_MIN_BLOCKS) k_project(ProjectArgs
     const float ndcx = hx * pw, ndcy = hy * pw;
 
     float c3[6];
-    const float o = __ldg(a.opac + i);     // with the other parameter loads: one round trip instead of two
+    const float o = cur.o;
     if (a.cov3d_precomp) {
 #pragma unroll
       for (int k = 0; k < 6; k++) c3[k] = __ldg(a.cov3d_precomp + 6 * (size_t)i + k);
     } else {
-      const float3 s = make_float3(__ldg(a.scales + 3 * i), __ldg(a.scales + 3 * i + 1), __ldg(a.scales + 3 * i + 2));
-      const float4 q = __ldg(reinterpret_cast<const float4*>(a.rots) + i);
-      cov3d_from_scale_rot(s, a.scale_modifier, q, c3);
+      cov3d_from_scale_rot(cur.s, a.scale_modifier, cur.q, c3);
     }
     Ewa e;
     ewa_jacobian(c, mu, (float)a.W, (float)a.H, a.tanfovx, a.tanfovy, e);
@@ -272,6 +321,7 @@ __global__ void __launch_bounds__(256, PROJECT_MIN_BLOCKS) k_project(ProjectArgs
   a.radii[i] = radius;
   a.depth_key[i] = key;
   a.tiles[i] = tiles_word;
+  }
 }
 
 // ==================================================================================================
@@ -970,7 +1020,22 @@ void launch_project(const ProjectArgs& a, int deg, cudaStream_t st) {
     count_launch();
     return;
   }
-  const dim3 grid((a.P + 255) / 256), block(256);
+  // grid-stride kernel: PROJECT_MIN_BLOCKS resident CTAs per SM times a few "waves", so that every thread works on
+  // several Gaussians with the loads of the next one in flight (load_proj_in) and the tail stays short
+  static std::atomic<int> ctas_per_wave{0}, waves{0};
+  int cpw = ctas_per_wave.load(), nw = waves.load();
+  if (cpw == 0) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cpw = (sms > 0 ? sms : 148) * PROJECT_MIN_BLOCKS;
+    const char* e = getenv("B200GS_PROJECT_WAVES");     // 0: one Gaussian per thread (no look-ahead)
+    nw = e ? atoi(e) : PROJECT_WAVES;
+    ctas_per_wave.store(cpw);
+    waves.store(nw);
+  }
+  const int need = (a.P + 255) / 256;
+  const dim3 grid(nw > 0 ? std::min(need, cpw * nw) : need), block(256);
   switch (deg) {
     case -1: k_project<-1><<<grid, block, 0, st>>>(a); break;
     case 0: k_project<0><<<grid, block, 0, st>>>(a); break;

@@ -209,6 +209,8 @@ __global__ void __launch_bounds__(256) k_render_fwd(RenderArgs a) {
             last = c * CH + jj + 1;
           }
         }
+        // leave the list behind the record that finished the warp's last pixel (done only changes on the rare path)
+        if (__all_sync(0xffffffffu, done)) break;
       }
     }
     const int num_done = __syncthreads_count(done);
@@ -306,6 +308,8 @@ __global__ void __launch_bounds__(256) k_render_bwd(RenderBwdArgs a) {
   const float F = fin.x * gr + fin.y * gg + fin.z * gb +
                   fin.w * (__ldg(a.bg) * gr + __ldg(a.bg + 1) * gg + __ldg(a.bg + 2) * gb);
   float T = 1.f, R = 0.f;
+  // nothing at or behind the largest n_contrib of the WARP's pixels reaches any of them: not even tested
+  const uint32_t wmax = __reduce_max_sync(0xffffffffu, ncontrib);
 
   for (uint32_t c = 0; c < nchunks; c++) {
     const int s = c & 1;
@@ -313,11 +317,11 @@ __global__ void __launch_bounds__(256) k_render_bwd(RenderBwdArgs a) {
     const uint32_t cnt = min((uint32_t)CH, n - c * CH);
     const float4* st = sm[s];
     for (uint32_t base = 0; base < cnt; base += 32) {
-      // this pixel is finished once the list position passes its last contributor
-      if (__all_sync(0xffffffffu, c * CH + base >= ncontrib)) break;
+      // this warp is finished once the list position passes its last contributor
+      if (c * CH + base >= wmax) break;
       const uint32_t j = base + lane;
       bool hit = false;
-      if (j < cnt) {
+      if (j < cnt && c * CH + j < wmax) {
         const float4 q0 = st[j * REC_F4], q1 = st[j * REC_F4 + 1];
         hit = block_may_contribute(q0.x, q0.y, q0.z, q0.w, q1.x, q1.z, rx0, ry0, rx1, ry1);
         if (coarse && hit)

@@ -60,6 +60,9 @@ __device__ __forceinline__ Tile4 tile4_setup(int W, int H, int warp, int lane) {
 #ifndef R4_BWD_MINB
 #define R4_BWD_MINB 12
 #endif
+#ifndef R4_FWD_PAIRS
+#define R4_FWD_PAIRS 0
+#endif
 template <bool SLAB>
 __global__ void __launch_bounds__(R4_THREADS, R4_FWD_MINB) k_render_fwd4(RenderArgs a) {
   __shared__ __align__(128) float4 sm[R4_STAGES][R4_CH * REC_F4];
@@ -115,13 +118,13 @@ __global__ void __launch_bounds__(R4_THREADS, R4_FWD_MINB) k_render_fwd4(RenderA
   bool mine_done = all_done();
   float pyf = t.pyf;
   asm volatile("" : "+f"(pyf));   // keep the row coordinate in its register (ptxas would re-derive it per record)
-  auto eval = [&](const float4& q0, const float4& q1, const float4& q2, uint32_t c, uint32_t jj, auto clamp_tag) {
+  // alpha (0 where the record does not reach the pixel) and 1 - alpha of one record for the four pixels
+  auto alphas = [&](const float4& q0, const float4& q1, float2 (&alpha)[2], float2 (&one_m)[2], auto clamp_tag) {
     constexpr bool CLAMP = decltype(clamp_tag)::value;
     const RowTerms rt = row_terms(q0.z, q0.w, q1.x, q0.y - pyf);
     const float2 nx2 = make_float2(-q0.x, -q0.x), nhA2 = make_float2(-rt.hA, -rt.hA);
     const float2 bdy2 = make_float2(rt.bdy, rt.bdy), ncdy2 = make_float2(-rt.cdy2, -rt.cdy2);
     const float2 o2 = make_float2(q1.y, q1.y);
-    float2 alpha[2], one_m[2];
 #pragma unroll
     for (int h = 0; h < 2; h++) {
       const float2 ndx = __fadd2_rn(pxf2[h], nx2);
@@ -133,18 +136,29 @@ __global__ void __launch_bounds__(R4_THREADS, R4_FWD_MINB) k_render_fwd4(RenderA
       alpha[h] = make_float2(valid0 ? al.x : 0.f, valid1 ? al.y : 0.f);
       one_m[h] = __ffma2_rn(alpha[h], make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
     }
+  };
+  // a pixel's transmittance is exhausted by the record at `pos` (at most once per pixel): the record does not act on
+  // it (alpha := 0, the identity) and the pixel is retired; `nalpha` / `none_m` are those of a record evaluated ahead
+  // of time against the same pixels (two-record step below), which must not act on the retired pixel either
+  auto retire = [&](const float2& t0, const float2& t1, float2 (&alpha)[2], float2 (&one_m)[2], uint32_t pos,
+                    float2 (*nalpha)[2], float2 (*none_m)[2]) {
+#define B200GS_RETIRE(H, F, I, TV)                                                          \
+    if (TV < 0.0001f) {                                                                       \
+      alpha[H].F = 0.f; one_m[H].F = 1.f; nstop[I] = pos; pxf2[H].F = FIN;                    \
+      if (nalpha) { (*nalpha)[H].F = 0.f; (*none_m)[H].F = 1.f; }                            \
+    }
+    B200GS_RETIRE(0, x, 0, t0.x)
+    B200GS_RETIRE(0, y, 1, t0.y)
+    B200GS_RETIRE(1, x, 2, t1.x)
+    B200GS_RETIRE(1, y, 3, t1.y)
+#undef B200GS_RETIRE
+    mine_done = all_done();
+  };
+  auto apply = [&](float2 (&alpha)[2], float2 (&one_m)[2], const float4& q2, uint32_t pos, float2 (*nalpha)[2],
+                   float2 (*none_m)[2]) {
     {
       const float2 t0 = __fmul2_rn(T[0], one_m[0]), t1 = __fmul2_rn(T[1], one_m[1]);
-      if (fminf(fminf(t0.x, t0.y), fminf(t1.x, t1.y)) < 0.0001f) {
-        // a pixel's transmittance is exhausted by this record (at most once per pixel): the record does not act on
-        // it (alpha := 0, the identity) and the pixel is retired
-        const uint32_t pos = c * R4_CH + jj;
-        if (t0.x < 0.0001f) { alpha[0].x = 0.f; one_m[0].x = 1.f; nstop[0] = pos; pxf2[0].x = FIN; }
-        if (t0.y < 0.0001f) { alpha[0].y = 0.f; one_m[0].y = 1.f; nstop[1] = pos; pxf2[0].y = FIN; }
-        if (t1.x < 0.0001f) { alpha[1].x = 0.f; one_m[1].x = 1.f; nstop[2] = pos; pxf2[1].x = FIN; }
-        if (t1.y < 0.0001f) { alpha[1].y = 0.f; one_m[1].y = 1.f; nstop[3] = pos; pxf2[1].y = FIN; }
-        mine_done = all_done();
-      }
+      if (fminf(fminf(t0.x, t0.y), fminf(t1.x, t1.y)) < 0.0001f) retire(t0, t1, alpha, one_m, pos, nalpha, none_m);
     }
     const float2 cr2 = make_float2(q2.x, q2.x), cg2 = make_float2(q2.y, q2.y), cb2 = make_float2(q2.z, q2.z);
 #pragma unroll
@@ -156,6 +170,23 @@ __global__ void __launch_bounds__(R4_THREADS, R4_FWD_MINB) k_render_fwd4(RenderA
       T[h] = __fmul2_rn(T[h], one_m[h]);
     }
   };
+  auto eval = [&](const float4& q0, const float4& q1, const float4& q2, uint32_t c, uint32_t jj, auto clamp_tag) {
+    float2 alpha[2], one_m[2];
+    alphas(q0, q1, alpha, one_m, clamp_tag);
+    apply(alpha, one_m, q2, c * R4_CH + jj, nullptr, nullptr);
+  };
+#if R4_FWD_PAIRS
+  // Two records per step: both alphas are evaluated first (eight independent exp2 chains instead of four -- the
+  // kernel waits on its own dependent instructions, ncu: `wait` 2.65 cycles per issue), then applied in list order.
+  auto eval2 = [&](const float4& a0, const float4& a1, const float4& a2, uint32_t ja, const float4& b0, const float4& b1,
+                   const float4& b2, uint32_t jb, uint32_t c, auto clamp_tag) {
+    float2 alA[2], omA[2], alB[2], omB[2];
+    alphas(a0, a1, alA, omA, clamp_tag);
+    alphas(b0, b1, alB, omB, clamp_tag);
+    apply(alA, omA, a2, c * R4_CH + ja, &alB, &omB);
+    apply(alB, omB, b2, c * R4_CH + jb, nullptr, nullptr);
+  };
+#endif
 
   uint32_t c = 0;
   bool early = false;
@@ -182,6 +213,16 @@ __global__ void __launch_bounds__(R4_THREADS, R4_FWD_MINB) k_render_fwd4(RenderA
         mask &= mask - 1;
         const uint32_t jj = base + b;
         const float4 q0 = st[jj * REC_F4], q1 = st[jj * REC_F4 + 1], q2 = st[jj * REC_F4 + 2];
+#if R4_FWD_PAIRS
+        if (mask) {
+          const int b1 = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const uint32_t jk = base + b1;
+          const float4 p0 = st[jk * REC_F4], p1 = st[jk * REC_F4 + 1], p2 = st[jk * REC_F4 + 2];
+          if (q2.w < 0.f || p2.w < 0.f) eval2(q0, q1, q2, jj, p0, p1, p2, jk, c, std::true_type{});
+          else eval2(q0, q1, q2, jj, p0, p1, p2, jk, c, std::false_type{});
+        } else
+#endif
         if (q2.w < 0.f) eval(q0, q1, q2, c, jj, std::true_type{});
         else eval(q0, q1, q2, c, jj, std::false_type{});
         if (__all_sync(0xffffffffu, mine_done)) break;

@@ -19,7 +19,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     cams = bench.jittered_cameras(K + 3)
     blocks = torch.stack([torch.cat([c.viewmatrix.reshape(-1), c.projmatrix.reshape(-1), c.campos.reshape(-1)]) for c in cams]).to(dev)
     bg = torch.zeros(3, device=dev)
-    r = SceneRenderer(tens, 3, bg, 1080, 1920, streams=4, graphs=True, host_frames=False)
+    r = SceneRenderer(tens, 3, bg, 1080, 1920, streams=int(os.environ.get('AB_STREAMS', '4')), graphs=True, host_frames=False)
     pend = []
     def sweep(n):
         for s in range(n):
