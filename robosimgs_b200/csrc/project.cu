@@ -22,6 +22,9 @@ namespace b200gs {
 #ifndef PROJECT_WAVES
 #define PROJECT_WAVES 2
 #endif
+#ifndef PROJECT_DENSE_WAVES
+#define PROJECT_DENSE_WAVES 1
+#endif
 #ifndef PROJECT_BWD_MIN_BLOCKS
 #define PROJECT_BWD_MIN_BLOCKS 3
 #endif
@@ -325,66 +328,125 @@ __global__ void __launch_bounds__(256, PROJECT_MIN_BLOCKS) k_project(ProjectArgs
 }
 
 // ==================================================================================================
-// K1 with DENSE WARPS.  Only a third of a scene's Gaussians survive the cull, scattered at random over the index
-// space, so in k_project above every warp walks the whole visible path with a third of its lanes (ncu: 28.6 M
-// warp-instructions on C3, long-scoreboard bound: the 12 SH loads of a lane are issued behind three dependent round
-// trips).  Here a warp owns PC_CHUNK = 128 consecutive Gaussians and works in three stages with a warp-private queue
-// in shared memory between them (ballot + popc compaction, __syncwarp only, no block barrier):
-//   1. cull: view depth of 4 Gaussians per lane (12 independent loads), defaults for the culled ones;
-//   2. geometry for the survivors, 32 at a time: conic, radius, rect, tight spans, bucket counters, record q0/q1;
-//   3. colour for those that touch a bin, 32 at a time: the 12 x 128-bit SH loads of all 32 lanes in flight at once.
-// Same arithmetic per Gaussian as k_project, bit for bit (option "project": 1 = this kernel, 0 = k_project, default).
-// Measured on C3 (B200, ncu): 24.3 M instead of 28.6 M warp-instructions -- the near-plane cull only removes 45 % of
-// the Gaussians and the geometry stage (spans, sqrt/rcp) dominates -- at 34 % instead of 43 % occupancy (72 registers,
-// two queues): 0.061-0.070 ms against 0.061 ms.  Kept as the second implementation the parity tests cross-check.
+// K1 with DENSE WARPS (option "project" = 1; the default is k_project above).  Only a third of a scene's Gaussians
+// reach the image, scattered at random over the index space, so in k_project every warp walks the whole visible path
+// with a third of its lanes (ncu: 28 M warp-instructions on C3 at 67 % issue-active once the loads are off the critical
+// path).  Here a warp owns PD_CHUNK consecutive Gaussians per step of a grid-stride loop and works in stages, with
+// warp-private queues in shared memory between them (ballot + popc compaction, __syncwarp only, no block barrier):
+//   0. the chunk's dense parameters (44 B per Gaussian) arrive in shared memory by coalesced 16-byte LDGSTS; the
+//      lines of the warp's NEXT chunk are prefetched to L2 at the same time;
+//   1. cull: near plane, then a CONSERVATIVE screen test -- radius <= 3 sqrt(|J|_F^2 |W|^2 |R|^2 s_max^2 + 0.62) + 1
+//      from the Jacobian's Frobenius norm and the largest scale (on C3 it passes 37.5 % of the Gaussians against
+//      37.0 % that really reach the image); the culled ones get their defaults, the survivors join the GEOMETRY QUEUE
+//      with their parameters;
+//   2. geometry for FULL batches of 32 queued Gaussians (the remainder is carried to the warp's next chunk): conic,
+//      radius, exact rect test, tight spans, bucket counters, record q0/q1, L2 prefetch of the SH row; those that
+//      touch a bin join the COLOUR QUEUE;
+//   3. colour, again 32 at a time: the 12 x 128-bit SH loads of all 32 lanes in flight at once.
+// Same expressions per Gaussian as k_project (the compiler contracts them per kernel: records agree to the last bit
+// or two, radii and pair lists exactly -- tested).
+// Measured on C3 (B200): every lane busy, but the kernel got SLOWER -- 0.058 ms (chunk 32) / 0.063 (chunk 64) against
+// 0.047 ms for k_project; a first version without carried queues (one index queue per chunk, 62 % of the lanes busy
+// in the geometry stage, 26.0 M warp-instructions instead of 28.0 M) took 0.052 ms.  The stages of a warp are strictly
+// serial (copy -> cull -> geometry -> colour), each with its own exposed L2 latency, and the cull + queue traffic cost
+// what the dense lanes save.  Kept as the second implementation the parity tests cross-check.
 // ==================================================================================================
-constexpr int PC_CHUNK = 128;
-constexpr int PC_WARPS = 4;
+#ifndef PROJECT_DENSE_CHUNK
+#define PROJECT_DENSE_CHUNK 32
+#endif
+constexpr int PD_CHUNK = PROJECT_DENSE_CHUNK;       // 32 or 64
+constexpr int PD_WARPS = 4;
+constexpr int PD_GQ = PD_CHUNK + 32;      // geometry queue: up to 31 carried entries + one chunk of survivors
+constexpr int PD_CQ = 64;                 // colour queue: up to 31 carried entries + one batch
+#ifndef PROJECT_DENSE_MIN_BLOCKS
+#define PROJECT_DENSE_MIN_BLOCKS 6
+#endif
 
 template <int DEG>
-__global__ void __launch_bounds__(32 * PC_WARPS) k_project_compact(ProjectArgs a) {
-  __shared__ uint8_t s_q1[PC_WARPS][PC_CHUNK];
-  __shared__ uint32_t s_q2[PC_WARPS][PC_CHUNK];
+__global__ void __launch_bounds__(32 * PD_WARPS, PROJECT_DENSE_MIN_BLOCKS) k_project_dense(ProjectArgs a) {
+  __shared__ __align__(16) float s_mu[PD_WARPS][PD_CHUNK * 3];
+  __shared__ __align__(16) float s_sc[PD_WARPS][PD_CHUNK * 3];
+  __shared__ __align__(16) float4 s_rot[PD_WARPS][PD_CHUNK];
+  __shared__ __align__(16) float s_op[PD_WARPS][PD_CHUNK];
+  __shared__ __align__(16) float4 s_gq[PD_WARPS][PD_GQ][3];   // {mu, o} {s, id} {q}
+  __shared__ __align__(16) float4 s_cq[PD_WARPS][PD_CQ];      // {mu, id}
+  __shared__ uint32_t s_cm[PD_WARPS][PD_CQ];                  // radius | general << 31
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int base = (blockIdx.x * PC_WARPS + warp) * PC_CHUNK;
-  if (base >= a.P) return;
+  const int nchunks = (a.P + PD_CHUNK - 1) / PD_CHUNK;
+  const int wstride = gridDim.x * PD_WARPS;
+  int chunk = blockIdx.x * PD_WARPS + warp;
+  if (chunk >= nchunks) return;
   CamConst c;
   load_cam(c, a.view, a.proj, a.campos);
   const uint32_t lt = (1u << lane) - 1u;
+  const bool vec16 = ((reinterpret_cast<uintptr_t>(a.means) | reinterpret_cast<uintptr_t>(a.scales) |
+                       reinterpret_cast<uintptr_t>(a.opac)) & 15u) == 0u;
+  // |W|_2^2 of the view rotation: 1 for a rigid camera (checked), its Frobenius norm otherwise
+  float wr2;
+  {
+    const float d00 = c.v[0] * c.v[0] + c.v[1] * c.v[1] + c.v[2] * c.v[2];
+    const float d11 = c.v[4] * c.v[4] + c.v[5] * c.v[5] + c.v[6] * c.v[6];
+    const float d22 = c.v[8] * c.v[8] + c.v[9] * c.v[9] + c.v[10] * c.v[10];
+    const float d01 = c.v[0] * c.v[4] + c.v[1] * c.v[5] + c.v[2] * c.v[6];
+    const float d02 = c.v[0] * c.v[8] + c.v[1] * c.v[9] + c.v[2] * c.v[10];
+    const float d12 = c.v[4] * c.v[8] + c.v[5] * c.v[9] + c.v[6] * c.v[10];
+    const float dev = fmaxf(fmaxf(fabsf(d00 - 1.f), fabsf(d11 - 1.f)),
+                            fmaxf(fabsf(d22 - 1.f), fmaxf(fabsf(d01), fmaxf(fabsf(d02), fabsf(d12)))));
+    wr2 = (dev < 1e-4f) ? 1.001f : (d00 + d11 + d22);
+  }
+  const float fx = (float)a.W / (2.f * a.tanfovx), fy = (float)a.H / (2.f * a.tanfovy);
+  const float limx = 1.3f * a.tanfovx, limy = 1.3f * a.tanfovy;
+  const float xmax = 16.f * (float)a.gx, ymax = 16.f * (float)a.gy;
+  uint32_t ng = 0, nc = 0;       // entries waiting in the geometry / colour queue (warp-uniform)
 
-  // ---- stage 1: cull ----
-  uint32_t n1 = 0;
-  float vzs[PC_CHUNK / 32];
+  // ---- stage 3: colour of the first nv entries of the colour queue ----
+  auto colour_batch = [&](uint32_t nv) {
+    if ((uint32_t)lane < nv) {
+      const float4 g = s_cq[warp][lane];
+      const uint32_t meta = s_cm[warp][lane];
+      const int i = (int)__float_as_uint(g.w);
+      const float frad = (meta >> 31) ? -(float)(meta & 0x7FFFFFFFu) : (float)(meta & 0x7FFFFFFFu);
+      float rgb[3];
+      uint32_t clampbits = 0;
+      if constexpr (DEG < 0) {
+        rgb[0] = __ldg(a.colors_precomp + 3 * (size_t)i);
+        rgb[1] = __ldg(a.colors_precomp + 3 * (size_t)i + 1);
+        rgb[2] = __ldg(a.colors_precomp + 3 * (size_t)i + 2);
+      } else {
+        constexpr int NB = (DEG < 0 ? 0 : (DEG + 1) * (DEG + 1));
+        constexpr int NF = NB * 3;
+        float f[NF > 0 ? NF : 1];
+        load_sh_row<NF>(a.shs + (size_t)i * a.M * 3, a.sh_vec != 0, f);
+        float dx = g.x - c.cam[0], dy = g.y - c.cam[1], dz = g.z - c.cam[2];
+        const float inv = 1.f / sqrtf(dx * dx + dy * dy + dz * dz);
+        float b[NB > 0 ? NB : 1];
+        sh_basis<DEG>(dx * inv, dy * inv, dz * inv, b);
 #pragma unroll
-  for (int it = 0; it < PC_CHUNK / 32; it++) {
-    const int i = base + it * 32 + lane;
-    vzs[it] = -1.f;
-    if (i < a.P) {
-      const float mx = __ldg(a.means + 3 * (size_t)i), my = __ldg(a.means + 3 * (size_t)i + 1), mz = __ldg(a.means + 3 * (size_t)i + 2);
-      vzs[it] = c.v[2] * mx + c.v[6] * my + c.v[10] * mz + c.v[14];
+        for (int ch = 0; ch < 3; ch++) {
+          float acc = 0.f;
+#pragma unroll
+          for (int kk = 0; kk < NB; kk++) acc += b[kk] * f[3 * kk + ch];
+          acc += 0.5f;
+          if (acc < 0.f) clampbits |= (1u << ch);
+          rgb[ch] = fmaxf(acc, 0.f);
+        }
+      }
+      a.clamped[i] = (uint8_t)clampbits;
+      a.rec[(size_t)i * REC_F4 + 2] = make_float4(rgb[0], rgb[1], rgb[2], frad);
     }
-  }
-#pragma unroll
-  for (int it = 0; it < PC_CHUNK / 32; it++) {
-    const int i = base + it * 32 + lane;
-    const bool pass = i < a.P && vzs[it] > a.near_plane;
-    if (i < a.P && !pass) { a.radii[i] = 0; a.depth_key[i] = 0xFFFFFFFFu; a.tiles[i] = 0u; }
-    const uint32_t m = __ballot_sync(0xffffffffu, pass);
-    if (pass) s_q1[warp][n1 + __popc(m & lt)] = (uint8_t)(it * 32 + lane);
-    n1 += __popc(m);
-  }
-  __syncwarp();
-
-  // ---- stage 2: geometry ----
-  uint32_t n2 = 0;
-  for (uint32_t k0 = 0; k0 < n1; k0 += 32) {
-    const bool on = k0 + lane < n1;
-    const int i = base + (on ? (int)s_q1[warp][k0 + lane] : 0);
-    uint32_t key = 0xFFFFFFFFu, ntiles = 0, tiles_word = 0;
-    int radius = 0;
-    bool general = false;
-    if (on) {
-      const float3 mu = make_float3(__ldg(a.means + 3 * (size_t)i), __ldg(a.means + 3 * (size_t)i + 1), __ldg(a.means + 3 * (size_t)i + 2));
+  };
+  // ---- stage 2: geometry of nv entries of the geometry queue starting at `off`; survivors join the colour queue ----
+  auto geom_batch = [&](uint32_t off, uint32_t nv) {
+    uint32_t ntiles = 0, meta = 0;
+    float4 e0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    int i = 0;
+    if ((uint32_t)lane < nv) {
+      e0 = s_gq[warp][off + lane][0];
+      const float4 e1 = s_gq[warp][off + lane][1], e2 = s_gq[warp][off + lane][2];
+      i = (int)__float_as_uint(e1.w);
+      uint32_t key = 0xFFFFFFFFu, tiles_word = 0;
+      int radius = 0;
+      const float3 mu = make_float3(e0.x, e0.y, e0.z);
       const float vz = c.v[2] * mu.x + c.v[6] * mu.y + c.v[10] * mu.z + c.v[14];
       const float hx = c.p[0] * mu.x + c.p[4] * mu.y + c.p[8] * mu.z + c.p[12];
       const float hy = c.p[1] * mu.x + c.p[5] * mu.y + c.p[9] * mu.z + c.p[13];
@@ -392,14 +454,7 @@ __global__ void __launch_bounds__(32 * PC_WARPS) k_project_compact(ProjectArgs a
       const float pw = 1.f / (hw + 0.0000001f);
       const float ndcx = hx * pw, ndcy = hy * pw;
       float c3[6];
-      if (a.cov3d_precomp) {
-#pragma unroll
-        for (int k = 0; k < 6; k++) c3[k] = __ldg(a.cov3d_precomp + 6 * (size_t)i + k);
-      } else {
-        const float3 s = make_float3(__ldg(a.scales + 3 * (size_t)i), __ldg(a.scales + 3 * (size_t)i + 1), __ldg(a.scales + 3 * (size_t)i + 2));
-        const float4 q = __ldg(reinterpret_cast<const float4*>(a.rots) + i);
-        cov3d_from_scale_rot(s, a.scale_modifier, q, c3);
-      }
+      cov3d_from_scale_rot(make_float3(e1.x, e1.y, e1.z), a.scale_modifier, e2, c3);
       Ewa e;
       ewa_jacobian(c, mu, (float)a.W, (float)a.H, a.tanfovx, a.tanfovy, e);
       float ca, cb, cc;
@@ -417,19 +472,24 @@ __global__ void __launch_bounds__(32 * PC_WARPS) k_project_compact(ProjectArgs a
         const TileRect r = reference_rect(px, py, irad, a.gx, a.gy);
         if ((r.x1 - r.x0) * (r.y1 - r.y0) != 0) {
           radius = irad;
-          const float o = __ldg(a.opac + i);
+          if constexpr (DEG > 0) {
+            const char* row = reinterpret_cast<const char*>(a.shs + (size_t)i * a.M * 3);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 128));
+          }
+          const float o = e0.w;
           const float thr = __logf(255.f * o) + 0.01f;
-          uint32_t* cnt = nullptr;
+          uint32_t* bcnt = nullptr;
           if (a.bucket_count) {
             const uint32_t db = __float_as_uint(vz);
             const uint32_t rel = db > a.near_bits ? db - a.near_bits : 0u;
-            cnt = a.bucket_count + min(rel >> a.slice_shift, (1u << a.slices_log2) - 1u);
+            bcnt = a.bucket_count + min(rel >> a.slice_shift, (1u << a.slices_log2) - 1u);
           }
-          ntiles = (o > 0.f) ? count_tiles(px, py, A, B, C, thr, bin_rect(r, a.bin_shift), a.bin_shift, cnt, a.slices_log2, a.gbx,
+          ntiles = (o > 0.f) ? count_tiles(px, py, A, B, C, thr, bin_rect(r, a.bin_shift), a.bin_shift, bcnt, a.slices_log2, a.gbx,
                                            a.pack_tiles != 0, &tiles_word) : 0u;
           if (ntiles > 0) {
             key = __float_as_uint(vz);
-            general = record_is_general(A, B, C, o);
+            meta = (uint32_t)irad | (record_is_general(A, B, C, o) ? 0x80000000u : 0u);
             float4* rec = a.rec + (size_t)i * REC_F4;
             rec[0] = make_float4(px, py, A, B);
             rec[1] = make_float4(C, o, thr, __uint_as_float((uint32_t)i));
@@ -441,46 +501,127 @@ __global__ void __launch_bounds__(32 * PC_WARPS) k_project_compact(ProjectArgs a
       a.tiles[i] = tiles_word;
     }
     const uint32_t m = __ballot_sync(0xffffffffu, ntiles > 0);
-    if (ntiles > 0) s_q2[warp][n2 + __popc(m & lt)] = (uint32_t)(i - base) | ((uint32_t)radius << 8) | (general ? 0x80000000u : 0u);
-    n2 += __popc(m);
-  }
-  __syncwarp();
+    if (ntiles > 0) {
+      const uint32_t slot = nc + __popc(m & lt);
+      s_cq[warp][slot] = make_float4(e0.x, e0.y, e0.z, __uint_as_float((uint32_t)i));
+      s_cm[warp][slot] = meta;
+    }
+    nc += __popc(m);
+    __syncwarp();
+    if (nc >= 32u) {
+      colour_batch(32u);
+      const uint32_t left = nc - 32u;
+      float4 tg = make_float4(0.f, 0.f, 0.f, 0.f);
+      uint32_t tm = 0;
+      if ((uint32_t)lane < left) { tg = s_cq[warp][32 + lane]; tm = s_cm[warp][32 + lane]; }
+      __syncwarp();
+      if ((uint32_t)lane < left) { s_cq[warp][lane] = tg; s_cm[warp][lane] = tm; }
+      nc = left;
+      __syncwarp();
+    }
+  };
 
-  // ---- stage 3: colour ----
-  for (uint32_t k0 = 0; k0 < n2; k0 += 32) {
-    if (k0 + lane >= n2) continue;
-    const uint32_t ent = s_q2[warp][k0 + lane];
-    const int i = base + (int)(ent & 255u);
-    const float frad = (ent >> 31) ? -(float)((ent >> 8) & 0x7FFFFFu) : (float)((ent >> 8) & 0x7FFFFFu);
-    float rgb[3];
-    uint32_t clampbits = 0;
-    if constexpr (DEG < 0) {
-      rgb[0] = __ldg(a.colors_precomp + 3 * (size_t)i);
-      rgb[1] = __ldg(a.colors_precomp + 3 * (size_t)i + 1);
-      rgb[2] = __ldg(a.colors_precomp + 3 * (size_t)i + 2);
+  for (; chunk < nchunks; chunk += wstride) {
+    const int base = chunk * PD_CHUNK;
+    const int cnt = min(PD_CHUNK, a.P - base);
+    // ---- stage 0: chunk -> shared memory ----
+    if (vec16 && cnt == PD_CHUNK) {
+      const float4* gm = reinterpret_cast<const float4*>(a.means + 3 * (size_t)base);
+      const float4* gs = reinterpret_cast<const float4*>(a.scales + 3 * (size_t)base);
+      const float4* gq = reinterpret_cast<const float4*>(a.rots) + base;
+      const float4* go = reinterpret_cast<const float4*>(a.opac + base);
+      float4* dm = reinterpret_cast<float4*>(s_mu[warp]);
+      float4* ds = reinterpret_cast<float4*>(s_sc[warp]);
+      float4* dop = reinterpret_cast<float4*>(s_op[warp]);
+#pragma unroll
+      for (int e = lane; e < PD_CHUNK * 3 / 4; e += 32) { cp_async16(dm + e, gm + e); cp_async16(ds + e, gs + e); }
+#pragma unroll
+      for (int e = lane; e < PD_CHUNK; e += 32) cp_async16(s_rot[warp] + e, gq + e);
+      if (lane < PD_CHUNK / 4) cp_async16(dop + lane, go + lane);
     } else {
-      constexpr int NB = (DEG < 0 ? 0 : (DEG + 1) * (DEG + 1));
-      constexpr int NF = NB * 3;
-      float f[NF > 0 ? NF : 1];
-      load_sh_row<NF>(a.shs + (size_t)i * a.M * 3, a.sh_vec != 0, f);
-      const float3 mu = make_float3(__ldg(a.means + 3 * (size_t)i), __ldg(a.means + 3 * (size_t)i + 1), __ldg(a.means + 3 * (size_t)i + 2));
-      float dx = mu.x - c.cam[0], dy = mu.y - c.cam[1], dz = mu.z - c.cam[2];
-      const float inv = 1.f / sqrtf(dx * dx + dy * dy + dz * dz);
-      float b[NB > 0 ? NB : 1];
-      sh_basis<DEG>(dx * inv, dy * inv, dz * inv, b);
-#pragma unroll
-      for (int ch = 0; ch < 3; ch++) {
-        float acc = 0.f;
-#pragma unroll
-        for (int k = 0; k < NB; k++) acc += b[k] * f[3 * k + ch];
-        acc += 0.5f;
-        if (acc < 0.f) clampbits |= (1u << ch);
-        rgb[ch] = fmaxf(acc, 0.f);
+      for (int e = lane; e < cnt * 3; e += 32) {
+        cp_async4(&s_mu[warp][e], a.means + 3 * (size_t)base + e);
+        cp_async4(&s_sc[warp][e], a.scales + 3 * (size_t)base + e);
+      }
+      for (int e = lane; e < cnt; e += 32) {
+        cp_async16(&s_rot[warp][e], reinterpret_cast<const float4*>(a.rots) + base + e);
+        cp_async4(&s_op[warp][e], a.opac + base + e);
       }
     }
-    a.clamped[i] = (uint8_t)clampbits;
-    a.rec[(size_t)i * REC_F4 + 2] = make_float4(rgb[0], rgb[1], rgb[2], frad);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    {   // the warp's next chunk: 44 B per Gaussian in lines of 128 B towards L2
+      constexpr int LM = PD_CHUNK * 12 / 128, LR = PD_CHUNK * 16 / 128, LO = (PD_CHUNK * 4 + 127) / 128;
+      const int nb = base + wstride * PD_CHUNK;
+      if (nb + PD_CHUNK <= a.P && lane < 2 * LM + LR + LO) {
+        const char* ptr = lane < LM       ? reinterpret_cast<const char*>(a.means + 3 * (size_t)nb) + 128 * lane
+                          : lane < 2 * LM ? reinterpret_cast<const char*>(a.scales + 3 * (size_t)nb) + 128 * (lane - LM)
+                          : lane < 2 * LM + LR ? reinterpret_cast<const char*>(reinterpret_cast<const float4*>(a.rots) + nb) + 128 * (lane - 2 * LM)
+                                               : reinterpret_cast<const char*>(a.opac + nb) + 128 * (lane - 2 * LM - LR);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+
+    // ---- stage 1: cull; survivors join the geometry queue with their parameters ----
+#pragma unroll
+    for (int it = 0; it < PD_CHUNK / 32; it++) {
+      const int k = it * 32 + lane;
+      bool pass = false;
+      float mx = 0.f, my = 0.f, mz = 0.f;
+      if (k < cnt) {
+        mx = s_mu[warp][3 * k]; my = s_mu[warp][3 * k + 1]; mz = s_mu[warp][3 * k + 2];
+        const float tz = c.v[2] * mx + c.v[6] * my + c.v[10] * mz + c.v[14];
+        if (tz > a.near_plane) {
+          pass = true;
+          const float hx = c.p[0] * mx + c.p[4] * my + c.p[8] * mz + c.p[12];
+          const float hy = c.p[1] * mx + c.p[5] * my + c.p[9] * mz + c.p[13];
+          const float hw = c.p[3] * mx + c.p[7] * my + c.p[11] * mz + c.p[15];
+          const float pw = rcp_fast(hw + 0.0000001f);
+          const float px = ((hx * pw + 1.f) * (float)a.W - 1.f) * 0.5f;
+          const float py = ((hy * pw + 1.f) * (float)a.H - 1.f) * 0.5f;
+          const float tx = c.v[0] * mx + c.v[4] * my + c.v[8] * mz + c.v[12];
+          const float ty = c.v[1] * mx + c.v[5] * my + c.v[9] * mz + c.v[13];
+          const float itz = rcp_fast(tz);
+          const float txc = fminf(limx, fmaxf(-limx, tx * itz)), tyc = fminf(limy, fmaxf(-limy, ty * itz));
+          const float jf2 = (fx * fx * (1.f + txc * txc) + fy * fy * (1.f + tyc * tyc)) * itz * itz;
+          const float smax = a.scale_modifier * fmaxf(fabsf(s_sc[warp][3 * k]), fmaxf(fabsf(s_sc[warp][3 * k + 1]), fabsf(s_sc[warp][3 * k + 2])));
+          const float4 q = s_rot[warp][k];
+          const float qn = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
+          const float rn = (fabsf(qn - 1.f) < 1e-4f) ? 1.001f : (1.f + 2.f * qn);
+          const float lam = jf2 * wr2 * (rn * rn) * (smax * smax) * 1.01f + 0.62f;
+          const float rb = 3.f * sqrt_approx(lam) * 1.001f + 1.6f;      // >= ceil(3 sqrt(lambda_1)) + 0.5 px of slack
+          // the reference rect is empty when px + r < 1 or px - r >= 16 gx (same in y): certain here -> radius 0
+          if (px + rb < 1.f || px - rb >= xmax || py + rb < 1.f || py - rb >= ymax) pass = false;
+        }
+        if (!pass) { a.radii[base + k] = 0; a.depth_key[base + k] = 0xFFFFFFFFu; a.tiles[base + k] = 0u; }
+      }
+      const uint32_t m = __ballot_sync(0xffffffffu, pass);
+      if (pass) {
+        float4* e = s_gq[warp][ng + __popc(m & lt)];
+        e[0] = make_float4(mx, my, mz, s_op[warp][k]);
+        e[1] = make_float4(s_sc[warp][3 * k], s_sc[warp][3 * k + 1], s_sc[warp][3 * k + 2], __uint_as_float((uint32_t)(base + k)));
+        e[2] = s_rot[warp][k];
+      }
+      ng += __popc(m);
+    }
+    __syncwarp();
+    // ---- stage 2 on full batches; the remainder (< 32 entries) is carried to the warp's next chunk ----
+    uint32_t off = 0;
+    for (; ng - off >= 32u; off += 32u) geom_batch(off, 32u);
+    if (off) {
+      const uint32_t left = ng - off;
+      float4 t0, t1, t2;
+      if ((uint32_t)lane < left) { t0 = s_gq[warp][off + lane][0]; t1 = s_gq[warp][off + lane][1]; t2 = s_gq[warp][off + lane][2]; }
+      __syncwarp();
+      if ((uint32_t)lane < left) { s_gq[warp][lane][0] = t0; s_gq[warp][lane][1] = t1; s_gq[warp][lane][2] = t2; }
+      ng = left;
+    }
+    __syncwarp();     // queues and the parameter stage are rewritten by the next step
   }
+  // ---- flush ----
+  if (ng) geom_batch(0u, ng);
+  if (nc) colour_batch(nc);
 }
 
 // ==================================================================================================
@@ -1008,14 +1149,31 @@ static bool use_project_compact() {
 
 void launch_project(const ProjectArgs& a, int deg, cudaStream_t st) {
   if (a.P == 0) return;
-  if (use_project_compact()) {
-    const dim3 grid((a.P + PC_CHUNK * PC_WARPS - 1) / (PC_CHUNK * PC_WARPS)), block(32 * PC_WARPS);
+  static std::atomic<int> sm_count{0};
+  int sms = sm_count.load();
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    sm_count.store(sms);
+  }
+  if (use_project_compact() && !a.cov3d_precomp) {     // (precomputed covariances: k_project)
+    const int need = (a.P + PD_CHUNK * PD_WARPS - 1) / (PD_CHUNK * PD_WARPS);
+    static std::atomic<int> dwaves{-1};
+    int nw = dwaves.load();
+    if (nw < 0) {
+      const char* e = getenv("B200GS_PROJECT_DENSE_WAVES");
+      nw = e ? atoi(e) : PROJECT_DENSE_WAVES;
+      dwaves.store(nw);
+    }
+    const dim3 grid(nw > 0 ? std::min(need, sms * PROJECT_DENSE_MIN_BLOCKS * nw) : need), block(32 * PD_WARPS);
     switch (deg) {
-      case -1: k_project_compact<-1><<<grid, block, 0, st>>>(a); break;
-      case 0: k_project_compact<0><<<grid, block, 0, st>>>(a); break;
-      case 1: k_project_compact<1><<<grid, block, 0, st>>>(a); break;
-      case 2: k_project_compact<2><<<grid, block, 0, st>>>(a); break;
-      default: k_project_compact<3><<<grid, block, 0, st>>>(a); break;
+      case -1: k_project_dense<-1><<<grid, block, 0, st>>>(a); break;
+      case 0: k_project_dense<0><<<grid, block, 0, st>>>(a); break;
+      case 1: k_project_dense<1><<<grid, block, 0, st>>>(a); break;
+      case 2: k_project_dense<2><<<grid, block, 0, st>>>(a); break;
+      default: k_project_dense<3><<<grid, block, 0, st>>>(a); break;
     }
     count_launch();
     return;
