@@ -30,6 +30,8 @@
 //
 // Four launches behind the projection kernel, no scan over Gaussians, no padding of a speculative capacity, no ranges pass, no tie repair.
 #include <algorithm>
+#include <atomic>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -157,6 +159,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_bucket_scan(BucketArgs a) {
 // ---- k_emit_bucket / k_emit_bucket_big ------------------------------------------------------------
 constexpr uint32_t BUCKET_BIG_THRESHOLD = 12;   // bins; above this a whole warp emits the Gaussian
 constexpr int EMIT_WARPS = 8;
+#ifndef EMIT_WAVES
+#define EMIT_WAVES 2
+#endif
 constexpr int EMIT_STAGE = 32 * BUCKET_BIG_THRESHOLD;   // staged (bin, owner lane) entries per warp
 
 __device__ __forceinline__ uint32_t rel_depth(const BucketArgs& a, uint32_t depth_bits) {
@@ -169,6 +174,22 @@ __device__ __forceinline__ void emit_one(const BucketArgs& a, uint32_t bin, uint
   const uint32_t slot = atomicAdd(a.bucket_cursor + ((bin << a.slices_log2) + slice), 1u);
   if (slot < a.capacity) a.seg[slot] = key;
 }
+// The same with the store DEFERRED: the slot a cursor atomic returns is only needed by the 8-byte store, so a lane
+// parks (slot, key) and writes them out just before its next atomic -- by then the L2 round trip is over and the
+// loads of the warp's next 32 Gaussians are in flight behind it.
+struct PendingPair {
+  uint64_t key;
+  uint32_t slot;      // 0xFFFFFFFF: nothing parked
+};
+__device__ __forceinline__ void flush_pending(const BucketArgs& a, PendingPair& p) {
+  if (p.slot < a.capacity) a.seg[p.slot] = p.key;
+  p.slot = 0xFFFFFFFFu;
+}
+__device__ __forceinline__ void emit_deferred(const BucketArgs& a, PendingPair& p, uint32_t bin, uint32_t slice, uint64_t key) {
+  flush_pending(a, p);
+  p.slot = atomicAdd(a.bucket_cursor + ((bin << a.slices_log2) + slice), 1u);
+  p.key = key;
+}
 
 // A cursor increment is an L2 round trip (~0.5 us) and a Gaussian's bins depend on nothing, so a lane that
 // walked its own bins one atomic after the other would serialise up to 12 round trips while most lanes of the
@@ -176,12 +197,19 @@ __device__ __forceinline__ void emit_one(const BucketArgs& a, uint32_t bin, uint
 // traffic), then the warp drains the staged list 32 pairs per round, one atomic per lane.
 __global__ void __launch_bounds__(32 * EMIT_WARPS) k_emit_bucket(BucketArgs a) {
   __shared__ uint32_t stage[EMIT_WARPS][EMIT_STAGE];
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t tword = (r < a.P) ? a.tiles[r] : 0u;     // count, or a packed footprint of up to three bins
-  // the depth travels with the footprint word (one coalesced line each): loading it only once the footprint is known
-  // to be non-empty would put a second dependent round trip in front of the cursor atomics
-  const uint32_t dkey = (r < a.P) ? a.depth_key[r] : 0u;
+  const int stride = gridDim.x * blockDim.x;
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  // Grid-stride loop: the footprint word and the depth of a thread's NEXT Gaussian are loaded while it works on the
+  // current one (the depth travels with the footprint word, one coalesced line each: loading it only once the
+  // footprint is known to be non-empty would put a second dependent round trip in front of the cursor atomics).
+  uint32_t tword_n = (r < a.P) ? a.tiles[r] : 0u;     // count, or a packed footprint of up to three bins
+  uint32_t dkey_n = (r < a.P) ? a.depth_key[r] : 0u;
+  PendingPair pend{0ull, 0xFFFFFFFFu};
+  for (; r - lane < a.P; r += stride) {
+  const uint32_t tword = tword_n, dkey = dkey_n;
+  tword_n = (r + stride < a.P) ? a.tiles[r + stride] : 0u;
+  dkey_n = (r + stride < a.P) ? a.depth_key[r + stride] : 0u;
   uint32_t n = tiles_count(tword);
   const uint32_t big_lanes = __ballot_sync(0xffffffffu, n > BUCKET_BIG_THRESHOLD);
   if (n > BUCKET_BIG_THRESHOLD) n = 0;          // large footprints: emitted by the whole warp below
@@ -192,7 +220,7 @@ __global__ void __launch_bounds__(32 * EMIT_WARPS) k_emit_bucket(BucketArgs a) {
     if (lane >= d) incl += t;
   }
   const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-  if (total == 0 && big_lanes == 0u) return;
+  if (total == 0 && big_lanes == 0u) continue;
   uint32_t rel = 0;
   if (n && (tword & TILES_PACKED)) {
     // small footprint: the projection kernel left the bin ids in tiles[] -- no record load, no span arithmetic
@@ -223,7 +251,7 @@ __global__ void __launch_bounds__(32 * EMIT_WARPS) k_emit_bucket(BucketArgs a) {
     const uint32_t orel = __shfl_sync(0xffffffffu, rel, owner);
     const uint32_t oid = (uint32_t)(r - lane + owner);
     const uint32_t bin = e & 0xFFFFu;
-    if (k < total && bin != 0xFFFFu) emit_one(a, bin, slice_of(a, orel), ((uint64_t)orel << 32) | oid);
+    if (k < total && bin != 0xFFFFu) emit_deferred(a, pend, bin, slice_of(a, orel), ((uint64_t)orel << 32) | oid);
   }
   // large footprints (a few screen-filling splats): one Gaussian at a time, lanes take the bin rows, then the bins of
   // each row, in parallel -- so that one of them cannot serialise a lane for hundreds of atomics
@@ -247,6 +275,9 @@ __global__ void __launch_bounds__(32 * EMIT_WARPS) k_emit_bucket(BucketArgs a) {
       }
     }
   }
+  __syncwarp();      // the staged list is rewritten by the next step
+  }
+  flush_pending(a, pend);
 }
 
 // ---- k_bucket_sort: one warp per bucket, keys in registers ---------------------------------------------
@@ -495,7 +526,22 @@ void launch_bucket_scan(const BucketArgs& a, cudaStream_t st) {
 
 void launch_bucket_emit(const BucketArgs& a, cudaStream_t st) {
   if (a.P == 0 || a.capacity == 0) return;
-  k_emit_bucket<<<(a.P + 255) / 256, 256, 0, st>>>(a);
+  // grid-stride kernel: a few resident waves, so that every thread sees several Gaussians with the next one's loads
+  // in flight (B200GS_EMIT_WAVES=0: one Gaussian per thread)
+  static std::atomic<int> ctas{0}, waves{-1};
+  int cpw = ctas.load(), nw = waves.load();
+  if (cpw == 0) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cpw = (sms > 0 ? sms : 148) * 8;          // 8 CTAs of 256 threads per SM
+    const char* e = getenv("B200GS_EMIT_WAVES");
+    nw = e ? atoi(e) : EMIT_WAVES;
+    ctas.store(cpw);
+    waves.store(nw);
+  }
+  const int need = (a.P + 255) / 256;
+  k_emit_bucket<<<(nw > 0 ? std::min(need, cpw * nw) : need), 256, 0, st>>>(a);
   count_launch();
 }
 
