@@ -19,6 +19,9 @@ namespace b200gs {
 #ifndef PROJECT_MIN_BLOCKS
 #define PROJECT_MIN_BLOCKS 3
 #endif
+#ifndef PROJECT_SH_BULK_PREFETCH
+#define PROJECT_SH_BULK_PREFETCH 0
+#endif
 #ifndef PROJECT_WAVES
 #define PROJECT_WAVES 2
 #endif
@@ -272,8 +275,12 @@ __global__ void __launch_bounds__(256, PROJECT_MIN_BLOCKS) k_project(ProjectArgs
           // the splat is on screen: start its SH row (up to 192 B = two lines) towards L2 now, the span walk and
           // the bucket counters below hide the DRAM latency the 12 loads would otherwise wait for
           const char* row = reinterpret_cast<const char*>(a.shs + (size_t)i * a.M * 3);
+#if PROJECT_SH_BULK_PREFETCH
+          if (a.sh_vec) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(row), "r"(((DEG + 1) * (DEG + 1) * 12 + 15) & ~15) : "memory");
+#else
           asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
           asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 128));
+#endif
         }
         // 0.5*q <= thr  <=>  o*exp(-0.5 q) >= 1/255 ; slack keeps the test conservative
         const float thr = __logf(255.f * o) + 0.01f;

@@ -345,7 +345,7 @@ def main():
     ap.add_argument("--cameras", type=int, default=64)
     ap.add_argument("--gaussians", type=int, default=3_000_000)
     ap.add_argument("--streams", type=int, default=0, help="frames in flight per GPU (0: host_frames_in_flight)")
-    ap.add_argument("--repeat", type=int, default=4, help="passes over this rank's cameras inside the timed region")
+    ap.add_argument("--repeat", type=int, default=16, help="passes over this rank's cameras inside the timed region")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
