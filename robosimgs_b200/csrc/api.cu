@@ -244,7 +244,7 @@ static BinBuf carve_binning(char* base, int64_t D, int tile_bits, size_t* bytes,
   b.vals = c.take<uint32_t>(D);
   b.coop_hist = c.take<uint32_t>(coop_sort_hist_bytes() / sizeof(uint32_t));
   b.win_first = c.take<uint32_t>((size_t)D / BUCKET_WINDOW + BUCKET_BINS_MAX + 2);
-  b.big_segs = c.take<uint2>((size_t)D / 512 + 2);
+  b.big_segs = c.take<uint2>((size_t)D / WARP_SORT_MAX + 2);
   b.cub_temp_bytes = pair_sort_temp_bytes(D, 32 + tile_bits);
   b.cub_temp = c.take<char>(b.cub_temp_bytes);
   if (bytes) *bytes = c.bytes();

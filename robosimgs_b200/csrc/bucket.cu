@@ -352,7 +352,6 @@ __device__ __forceinline__ void sort_bucket_in_registers(const uint64_t* __restr
   }
 }
 
-constexpr uint32_t WARP_SORT_MAX = 512;
 constexpr int SORT_WARPS = 8;
 
 __global__ void __launch_bounds__(32 * SORT_WARPS) k_bucket_sort(BucketArgs a) {
@@ -374,7 +373,7 @@ __global__ void __launch_bounds__(32 * SORT_WARPS) k_bucket_sort(BucketArgs a) {
   else if (n <= 64) sort_bucket_in_registers<2>(seg, out, n, lane);
   else if (n <= 128) sort_bucket_in_registers<4>(seg, out, n, lane);
   else if (n <= 256) sort_bucket_in_registers<8>(seg, out, n, lane);
-  else sort_bucket_in_registers<16>(seg, out, n, lane);
+  else if (WARP_SORT_MAX > 256) sort_bucket_in_registers<(WARP_SORT_MAX > 256 ? 16 : 8)>(seg, out, n, lane);
   if (a.slab) {     // record slab for the TMA-fed compositing ring (option "slab"): slab[s + i] = rec[out[i]]
     __syncwarp();   // the ids this warp just wrote are visible to all its lanes
     float4* dst = a.slab + (size_t)s * REC_F4;

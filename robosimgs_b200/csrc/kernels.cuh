@@ -9,7 +9,14 @@ constexpr uint32_t BUCKETS_MAX = 512 * 1024;
 constexpr uint32_t BUCKET_BINS_MAX = 65536;   // table size; bin ids travel in 16 bits through the staged emission, so
                                               // the bucketed path serves images of up to 65534 bins
 constexpr int BUCKET_SLICES_LOG2_MAX = 13;
-constexpr uint32_t BUCKET_WINDOW = 192;   // pairs per sorter warp (cut at the next bucket boundary)
+#ifndef BUCKET_WINDOW_N
+#define BUCKET_WINDOW_N 192
+#endif
+#ifndef WARP_SORT_MAX_N
+#define WARP_SORT_MAX_N 512
+#endif
+constexpr uint32_t BUCKET_WINDOW = BUCKET_WINDOW_N;   // pairs per sorter warp (cut at the next bucket boundary)
+constexpr uint32_t WARP_SORT_MAX = WARP_SORT_MAX_N;   // largest window one warp sorts in registers; larger ones take the one-CTA path
 
 struct ProjectArgs {
   int P, M, W, H, gx, gy, sh_vec, bin_shift;
