@@ -48,6 +48,7 @@ extern "C" {
  * device->host copy of the camera.
  */
 #define B200GS_DEFER_PAIR_CHECK 1
+#define B200GS_FORWARD_ONLY 2
 #define B200GS_BIN_SHIFT_HINT(s) (((s) + 1) << 8)
 
 typedef struct B200GSParams {
@@ -67,6 +68,9 @@ typedef struct B200GSParams {
                              asynchronously on `stream`, and the CALLER checks D <= pair_capacity_hint once the
                              stream has passed the call (a frame that fails the check is incomplete and must be
                              rendered again).  Lets a sweep keep many independent frames in flight.
+                             bit 1 (B200GS_FORWARD_ONLY): no backward pass will follow this frame -- the per-pixel state
+                             the adjoint replays from (accumulated colour, final transmittance, list position: 20
+                             bytes per pixel of `img`) is not written; out_color and radii are unchanged.
                              bits 8..11 (B200GS_BIN_SHIFT_HINT(s) = (s + 1) << 8, 0 = none): pairs are binned per
                              (16 << s)^2 pixels for this call instead of the automatic choice -- a performance hint
                              (results are identical for every bin size); b200gs_backward must get the same bits. */

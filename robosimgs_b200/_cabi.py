@@ -23,6 +23,7 @@ EXPORTED_SYMBOLS = (
 )
 ADAM_MAX_GROUPS = 8
 DEFER_PAIR_CHECK = 1
+FORWARD_ONLY = 2
 NUM_STAGES = 8
 
 

@@ -631,7 +631,8 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
     RenderArgs ra;
     ra.W = W; ra.H = H; ra.gbx = gbx; ra.bin_shift = bs; ra.ranges = ib.ranges; ra.point_list = bb.vals_sorted;
     ra.rec = gb.rec; ra.slab = (slab && cap > 0) ? bb.slab : nullptr; ra.bg = bg; ra.out_color = out_color;
-    ra.pix = ib.pix; ra.n_contrib = ib.n_contrib;
+    const bool fwd_only = (prm->flags & B200GS_FORWARD_ONLY) != 0;     // nothing is kept for the adjoint
+    ra.pix = fwd_only ? nullptr : ib.pix; ra.n_contrib = fwd_only ? nullptr : ib.n_contrib;
     ra.vec4 = ((W & 3) == 0 && (reinterpret_cast<uintptr_t>(out_color) & 15) == 0) ? 1 : 0;
     {
       StageTimer t(5, st);
@@ -700,6 +701,10 @@ int b200gs_backward(const B200GSParams* prm, const float* bg, const float* viewm
   if ((rc = check_params(prm))) return rc;
   if ((rc = check_inputs(prm, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp))) return rc;
   const int P = prm->P, H = prm->image_height, W = prm->image_width;
+  if (prm->flags & B200GS_FORWARD_ONLY) {
+    set_error("backward: the forward call was B200GS_FORWARD_ONLY, the per-pixel state of the adjoint was not written");
+    return B200GS_ERR_INVALID_ARG;
+  }
   if (P == 0) return 0;
   if (!bg || !viewmatrix || !projmatrix || !campos || !radii || !geom || !img || !dL_dout_color ||
       !dL_dmeans3D || !dL_dmeans2D || !dL_dopacities || (num_rendered > 0 && !binning)) {

@@ -28,8 +28,22 @@ namespace b200gs {
 #ifndef PROJECT_DENSE_WAVES
 #define PROJECT_DENSE_WAVES 1
 #endif
+// SH row of the projection adjoint staged through the thread's slab row (LDGSTS issued with the first loads, read back
+// behind the geometry): measured on C3 0.0999 -> 0.1084 ms (128-thread CTAs) -- the kernel does not wait for that round
+// trip, and the copies cost shared-memory bandwidth.  Off.
+#ifndef PROJECT_BWD_STAGE_SH
+#define PROJECT_BWD_STAGE_SH 0
+#endif
+#ifndef PROJECT_BWD_EARLY_CLAMP    // clamp mask loaded with the first batch of loads: measured 0.1084 -> 0.1048 with staging on,
+#define PROJECT_BWD_EARLY_CLAMP 0  // 0.1065 -> 0.111 without (256-thread CTAs)
+#endif
+// CTA size of the projection adjoint (its SH-gradient slab is THREADS x M x 12 bytes and leaves behind ONE barrier):
+// 256 threads 0.1065 ms, 128 threads 0.0999 (same 24 warps per SM; the warps of a CTA wait for its slowest one)
+#ifndef PROJECT_BWD_THREADS
+#define PROJECT_BWD_THREADS 128
+#endif
 #ifndef PROJECT_BWD_MIN_BLOCKS
-#define PROJECT_BWD_MIN_BLOCKS 3
+#define PROJECT_BWD_MIN_BLOCKS (768 / PROJECT_BWD_THREADS)
 #endif
 
 struct CamConst {
@@ -863,7 +877,7 @@ __global__ void k_mark_visible(int P, const float* __restrict__ means, const flo
 // Every output element is written.
 // ==================================================================================================
 template <int DEG>
-__global__ void __launch_bounds__(256, PROJECT_BWD_MIN_BLOCKS) k_project_bwd(ProjectBwdArgs a) {
+__global__ void __launch_bounds__(PROJECT_BWD_THREADS, PROJECT_BWD_MIN_BLOCKS) k_project_bwd(ProjectBwdArgs a) {
   // SH-gradient rows of a block are contiguous in memory (256 rows x M*3 floats): with a.slab they are
   // staged in shared memory and leave the SM as ONE TMA bulk store (cp.async.bulk shared -> global)
   // instead of twelve 16-byte stores per thread at a 192-byte stride, whose half-written sectors cost
@@ -897,6 +911,25 @@ __global__ void __launch_bounds__(256, PROJECT_BWD_MIN_BLOCKS) k_project_bwd(Pro
       const char* row = reinterpret_cast<const char*>(a.shs + (size_t)i * a.M * 3);
       asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
       asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 128));
+    }
+#endif
+#if PROJECT_BWD_EARLY_CLAMP
+    const uint32_t cl = DEG >= 0 ? (uint32_t)a.clamped[i] : 0u;     // with the first batch of loads, not behind the geometry
+#endif
+#if PROJECT_BWD_STAGE_SH
+    // The SH row is only needed behind the geometry part, and holding its 12 x 128-bit loads in registers across that
+    // part does not fit: the compiler issues them late, a third dependent DRAM round trip.  With the slab the thread
+    // owns a 192-byte shared-memory row (its OUTPUT row): the input row is copied into it by LDGSTS right away -- no
+    // register holds it in flight --, read back behind the geometry and then overwritten with the gradient row.
+    const bool staged = use_slab && vec_ok && DEG >= 0;
+    if (staged) {
+      constexpr int NV_IN = (NB * 3 + 3) / 4;
+      const char* src = reinterpret_cast<const char*>(a.shs + (size_t)i * a.M * 3);
+      const uint32_t dst = smem_u32(sh_row);
+#pragma unroll
+      for (int v = 0; v < NV_IN; v++)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * v), "l"(src + 16 * v) : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
     }
 #endif
     CamConst c;
@@ -983,13 +1016,30 @@ __global__ void __launch_bounds__(256, PROJECT_BWD_MIN_BLOCKS) k_project_bwd(Pro
     if constexpr (DEG >= 0) {
       constexpr int NF = NB * 3;
       float f[NF > 0 ? NF : 1];
+#if PROJECT_BWD_STAGE_SH
+      if (staged) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");      // the thread's own copies: its row is complete
+        constexpr int NV_IN = (NF + 3) / 4;
+        const float4* r4 = reinterpret_cast<const float4*>(sh_row);
+#pragma unroll
+        for (int v = 0; v < NV_IN; v++) {
+          const float4 t4 = r4[v];
+          if (4 * v + 0 < NF) f[4 * v + 0] = t4.x;
+          if (4 * v + 1 < NF) f[4 * v + 1] = t4.y;
+          if (4 * v + 2 < NF) f[4 * v + 2] = t4.z;
+          if (4 * v + 3 < NF) f[4 * v + 3] = t4.w;
+        }
+      } else
+#endif
       load_sh_row<NF>(a.shs + (size_t)i * a.M * 3, vec_ok, f);
       const float dx = mu.x - c.cam[0], dy = mu.y - c.cam[1], dz = mu.z - c.cam[2];
       const float inv = 1.f / sqrtf(dx * dx + dy * dy + dz * dz);
       const float x = dx * inv, y = dy * inv, z = dz * inv;
       float b[NB > 0 ? NB : 1];
       sh_basis<DEG>(x, y, z, b);
+#if !PROJECT_BWD_EARLY_CLAMP
       const uint32_t cl = a.clamped[i];
+#endif
       float gc3[3];
 #pragma unroll
       for (int ch = 0; ch < 3; ch++) gc3[ch] = ((cl >> ch) & 1u) ? 0.f : gcol[ch];
@@ -1252,10 +1302,10 @@ void launch_extract_alpha(const float4* pix, size_t npx, float* out, cudaStream_
 void launch_project_bwd(const ProjectBwdArgs& a_in, int deg, cudaStream_t st) {
   if (a_in.P == 0) return;
   ProjectBwdArgs a = a_in;
-  const dim3 grid((a.P + 255) / 256), block(256);
+  const dim3 grid((a.P + PROJECT_BWD_THREADS - 1) / PROJECT_BWD_THREADS), block(PROJECT_BWD_THREADS);
   // SH-gradient slab through shared memory + TMA bulk store: rows must be 16-byte multiples and the slab
   // must fit the default 48 KB of dynamic shared memory (M <= 16)
-  const size_t slab_bytes = (size_t)256 * a.M * 12;
+  const size_t slab_bytes = (size_t)PROJECT_BWD_THREADS * a.M * 12;
   a.slab = (deg >= 0 && a.sh_vec && slab_bytes <= 48 * 1024 && a.slab >= 0 && !a.active_only) ? 1 : 0;
   const size_t sm = a.slab ? slab_bytes : 0;
   switch (deg) {

@@ -225,8 +225,10 @@ __global__ void __launch_bounds__(256) k_render_fwd(RenderArgs a) {
   if (inside) {
     const size_t pid = (size_t)py * a.W + px;
     const size_t hw = (size_t)a.H * a.W;
-    a.pix[pid] = make_float4(Cr, Cg, Cb, T);
-    a.n_contrib[pid] = last;
+    if (a.pix) {     // (null for forward-only frames)
+      a.pix[pid] = make_float4(Cr, Cg, Cb, T);
+      a.n_contrib[pid] = last;
+    }
     a.out_color[pid] = __fmaf_rn(T, __ldg(a.bg + 0), Cr);
     a.out_color[hw + pid] = __fmaf_rn(T, __ldg(a.bg + 1), Cg);
     a.out_color[2 * hw + pid] = __fmaf_rn(T, __ldg(a.bg + 2), Cb);

@@ -247,10 +247,12 @@ __global__ void __launch_bounds__(R4_THREADS, R4_FWD_MINB) k_render_fwd4(RenderA
   const size_t hw = (size_t)a.H * a.W;
   const size_t pid = (size_t)t.py * a.W + t.px0;
   if (a.vec4 && t.in[3]) {
-    float4* pix = a.pix + pid;
+    if (a.pix) {     // (null for forward-only frames: nothing is kept for the adjoint)
+      float4* pix = a.pix + pid;
 #pragma unroll
-    for (int i = 0; i < 4; i++) pix[i] = make_float4(R_[i], G_[i], B_[i], Tf[i]);
-    *reinterpret_cast<uint4*>(a.n_contrib + pid) = make_uint4(nstop[0], nstop[1], nstop[2], nstop[3]);
+      for (int i = 0; i < 4; i++) pix[i] = make_float4(R_[i], G_[i], B_[i], Tf[i]);
+      *reinterpret_cast<uint4*>(a.n_contrib + pid) = make_uint4(nstop[0], nstop[1], nstop[2], nstop[3]);
+    }
     const float b0 = __ldg(a.bg + 0), b1 = __ldg(a.bg + 1), b2 = __ldg(a.bg + 2);
     *reinterpret_cast<float4*>(a.out_color + pid) =
         make_float4(__fmaf_rn(Tf[0], b0, R_[0]), __fmaf_rn(Tf[1], b0, R_[1]), __fmaf_rn(Tf[2], b0, R_[2]),
@@ -265,8 +267,10 @@ __global__ void __launch_bounds__(R4_THREADS, R4_FWD_MINB) k_render_fwd4(RenderA
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       if (!t.in[i]) continue;
-      a.pix[pid + i] = make_float4(R_[i], G_[i], B_[i], Tf[i]);
-      a.n_contrib[pid + i] = nstop[i];
+      if (a.pix) {
+        a.pix[pid + i] = make_float4(R_[i], G_[i], B_[i], Tf[i]);
+        a.n_contrib[pid + i] = nstop[i];
+      }
       a.out_color[pid + i] = __fmaf_rn(Tf[i], __ldg(a.bg + 0), R_[i]);
       a.out_color[hw + pid + i] = __fmaf_rn(Tf[i], __ldg(a.bg + 1), G_[i]);
       a.out_color[2 * hw + pid + i] = __fmaf_rn(Tf[i], __ldg(a.bg + 2), B_[i]);

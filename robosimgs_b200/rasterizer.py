@@ -243,9 +243,16 @@ class DeferOptions(list):
     word that receives the pair count; record_event -- False inside stream capture (the caller records
     its own event after replaying the graph)."""
 
-    def __init__(self, capacity: int = 0, word=None, record_event: bool = True):
+    def __init__(self, capacity: int = 0, word=None, record_event: bool = True, train: bool = False):
         super().__init__()
         self.capacity, self.word, self.record_event = int(capacity), word, bool(record_event)
+        self.train = bool(train)      # the frame keeps its adjoint state; backward validates the ticket
+
+
+class PairCapacityExceeded(_cabi.B200GSError):
+    """A training step made with ``GaussianRasterizer.defer_pair_check`` produced more pairs than the speculative
+    capacity: the frame the loss saw was incomplete and so are the gradients.  The capacity hint has been raised;
+    run the step again (robosimgs_b200.train.render_step does)."""
 
 
 class _RasterizeGaussians(torch.autograd.Function):
@@ -281,16 +288,20 @@ class _RasterizeGaussians(torch.autograd.Function):
         # deferred pair check (forward-only callers that pass a ticket box): only once a hint exists
         ticket = None
         if ticket_box is not None:
-            if torch.is_grad_enabled() and any(ctx.needs_input_grad):
-                raise _cabi.B200GSError("the deferred pair check is for forward-only rendering (no_grad)")
             opts = ticket_box if isinstance(ticket_box, DeferOptions) else DeferOptions()
+            if torch.is_grad_enabled() and any(ctx.needs_input_grad) and not opts.train:
+                raise _cabi.B200GSError("the deferred pair check is for forward-only rendering (no_grad)")
             if opts.capacity > 0:
                 hint = opts.capacity
             ticket = PairTicket(hint if P > 0 else 0, hint_key, opts.word)
             ticket_box.append(ticket)
         defer = ticket is not None and hint > 0 and P > 0
         pol, shift_used, bin_flags = _bin_flags(hint_key, H, W)
-        prm = _params(P, M, rs, hint, near_plane, (_cabi.DEFER_PAIR_CHECK if defer else 0) | bin_flags)
+        # a deferred frame is forward-only by construction: the per-pixel state of the adjoint (20 B per pixel) is not
+        # written unless the caller wants the alpha channel, which is read from it
+        keep_state = want_alpha or (ticket_box is not None and opts.train)
+        fwd_flags = ((_cabi.DEFER_PAIR_CHECK | (0 if keep_state else _cabi.FORWARD_ONLY)) if defer else 0)
+        prm = _params(P, M, rs, hint, near_plane, fwd_flags | bin_flags)
         color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
         radii = torch.empty((P,), dtype=torch.int32, device=dev)
         num_rendered = C.c_int32(0)
@@ -317,7 +328,9 @@ class _RasterizeGaussians(torch.autograd.Function):
                                                    _ptr(alpha), stream))
         ctx.raster_settings = rs
         ctx.near_plane = near_plane
-        ctx.num_rendered = int(num_rendered.value)
+        # (a deferred training frame: the adjoint only needs to know that there are pairs; it validates the ticket)
+        ctx.num_rendered = int(hint) if defer else int(num_rendered.value)
+        ctx.ticket = ticket if (defer and opts.train) else None
         ctx.bin_flags = bin_flags
         if not defer:
             _PAIR_HINTS[hint_key] = max(ctx.num_rendered, int(last_D * 0.97))
@@ -382,6 +395,10 @@ class _RasterizeGaussians(torch.autograd.Function):
                 _ptr(g_sh), _ptr(g_col), _ptr(g_opac), _ptr(g_scales), _ptr(g_rots), _ptr(g_cov),
                 lease.allocs["scratch"], stream))
             lease.release()
+        if ctx.ticket is not None and not ctx.ticket.ok():
+            # everything above was launched for an incomplete frame (harmless: no kernel indexes past its buffers);
+            # the host only learns it here, with the whole step already queued -- it never waited inside the step
+            raise PairCapacityExceeded(f"{ctx.ticket.pairs} pairs, capacity {ctx.ticket.hint}: run the step again")
         # order of the public interface: means3D, means2D, sh, colors_precomp, opacities, scales,
         # rotations, cov3Ds_precomp, raster_settings
         sh_shape, opac_shape = ctx.in_shapes        # forward accepts shs [P, M*3] and opacities [P]: mirror them
@@ -392,9 +409,9 @@ class _RasterizeGaussians(torch.autograd.Function):
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
-                        cov3Ds_precomp, raster_settings, scratch_tag=None):
+                        cov3Ds_precomp, raster_settings, scratch_tag=None, ticket_box=None):
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
-                                     cov3Ds_precomp, raster_settings, torch.is_grad_enabled(), 0.0, False, None,
+                                     cov3Ds_precomp, raster_settings, torch.is_grad_enabled(), 0.0, False, ticket_box,
                                      scratch_tag)
 
 
@@ -403,6 +420,13 @@ class GaussianRasterizer(nn.Module):
         super().__init__()
         self.raster_settings = raster_settings
         self.scratch_tag = None      # not None: this rasterizer leases PRIVATE scratch (see _Lease)
+        # Training without a host wait inside the step (opt-in; the public operator's contract is a complete frame on
+        # return, so the default is off): forward launches the frame for the speculative pair capacity and returns at
+        # once, backward launches the adjoint and only THEN checks the pair count that has long arrived in a pinned
+        # word.  If it exceeded the capacity (an abrupt view change) backward raises PairCapacityExceeded and the
+        # caller repeats the step; `last_ticket` lets a caller that never runs backward validate the frame.
+        self.defer_pair_check = False
+        self.last_ticket = None
 
     def markVisible(self, positions: torch.Tensor) -> torch.Tensor:
         """Boolean mask of the Gaussians that pass the near-plane cull (view-space z > 0.2)."""
@@ -457,8 +481,14 @@ class GaussianRasterizer(nn.Module):
         scales = empty if scales is None else scales
         rotations = empty if rotations is None else rotations
         cov3D_precomp = empty if cov3D_precomp is None else cov3D_precomp
-        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
-                                   cov3D_precomp, rs, self.scratch_tag)
+        box = None
+        if self.defer_pair_check and torch.is_grad_enabled():
+            box = DeferOptions(train=True)
+        out = rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
+                                  cov3D_precomp, rs, self.scratch_tag, box)
+        if box is not None:
+            self.last_ticket = box[-1]
+        return out
 
 
 def export_rgb8(color: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:

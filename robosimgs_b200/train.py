@@ -53,6 +53,23 @@ class GradBucket:
             p.grad = v
 
 
+def backward_or_retry(loss_fn: Callable[..., torch.Tensor], *args, retries: int = 2) -> torch.Tensor:
+    """loss_fn(*args).backward() for a loss rendered through a GaussianRasterizer with ``defer_pair_check`` on: the
+    host never waits inside the step; if the frame turns out to have been incomplete (PairCapacityExceeded, raised by
+    the rasterizer's backward BEFORE any gradient reaches a leaf) the camera is simply rendered again -- the pair
+    capacity hint has been raised by then.  Returns the loss."""
+    from .rasterizer import PairCapacityExceeded
+    for attempt in range(retries + 1):
+        loss = loss_fn(*args)
+        try:
+            loss.backward()
+            return loss
+        except PairCapacityExceeded:
+            if attempt == retries:
+                raise
+    raise AssertionError("unreachable")
+
+
 def dp_train_step(params: Sequence[torch.Tensor], optimizer, cameras: Sequence,
                   loss_fn: Callable[[object], torch.Tensor], bucket: GradBucket) -> torch.Tensor:
     """One data-parallel step over a camera batch.
@@ -66,8 +83,7 @@ def dp_train_step(params: Sequence[torch.Tensor], optimizer, cameras: Sequence,
         p.grad = None
     total = None
     for cam in cameras[rank::world]:
-        loss = loss_fn(cam) / len(cameras)
-        loss.backward()
+        loss = backward_or_retry(lambda c: loss_fn(c) / len(cameras), cam)
         total = loss.detach() if total is None else total + loss.detach()
     bucket.pack()
     bucket.all_reduce(average=False)         # losses are already divided by the global batch size

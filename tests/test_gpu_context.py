@@ -28,12 +28,12 @@ class Ctx:
     def close(self):
         self.cabi.check(self.L.b200gs_context_destroy(self.h))
 
-    def forward(self, sc, rs, degree, defer=False):
+    def forward(self, sc, rs, degree, defer=False, flags=0):
         """sc: dict of CUDA tensors; rs: settings with CUDA tensors.  Context arenas for all scratch (NULL allocators)."""
         cabi, L = self.cabi, self.L
         P, M = sc["means3D"].shape[0], sc["shs"].shape[1]
         prm = cabi.B200GSParams(P, degree, M, rs.image_height, rs.image_width, rs.tanfovx, rs.tanfovy, rs.scale_modifier,
-                                0, 0, 0.0, 0, 0)
+                                0, 0, 0.0, flags, 0)
         color = torch.empty((3, rs.image_height, rs.image_width), device="cuda")
         radii = torch.empty(P, dtype=torch.int32, device="cuda")
         p = lambda t: C.c_void_p(t.data_ptr())
@@ -158,6 +158,18 @@ def test_context_backward_matches_oracle_and_bin_policy_never_changes_results():
             r = getattr(ref, k)
             assert max_rel_err(g[k].cpu().numpy().reshape(r.shape), r) < 1e-3, k
         assert max_rel_err(g2d.cpu().numpy(), ref.means2D) < 1e-3
+        # B200GS_FORWARD_ONLY travels through the context: same frame, same radii, and the adjoint refuses to run on it
+        color2, radii2, D2, _, flags2, prm2 = ctx.forward(dsc, rs, 1, flags=cabi.FORWARD_ONLY)
+        torch.cuda.synchronize()
+        assert flags2 == (flags1 | cabi.FORWARD_ONLY) and D2 == D1
+        assert torch.equal(color2, color1) and torch.equal(radii2, radii)
+        with pytest.raises(cabi.B200GSError, match="FORWARD_ONLY"):
+            cabi.check(L.b200gs_context_backward(ctx.h, C.byref(prm2), C.c_int32(flags2), p(rs.bg), p(rs.viewmatrix),
+                                                 p(rs.projmatrix), p(rs.campos), p(dsc["means3D"]), p(dsc["shs"]), None,
+                                                 p(dsc["opacities"]), p(dsc["scales"]), p(dsc["rotations"]), None, p(radii2),
+                                                 None, None, None, C.c_int32(D2), p(dL), p(g["means3D"]), p(g2d), p(g["shs"]),
+                                                 None, p(g["opacities"]), p(g["scales"]), p(g["rotations"]), None,
+                                                 C.c_void_p(torch.cuda.current_stream().cuda_stream)))
     finally:
         ctx.close()
 

@@ -288,6 +288,70 @@ def test_deferred_pair_check_ticket_protocol():
         rasterizer.ADAPT_BIN_SIZE = True
 
 
+def test_training_step_with_deferred_pair_check_matches_oracle_and_recovers_from_overflow():
+    """GaussianRasterizer.defer_pair_check (opt-in): forward returns without waiting for the pair count, backward
+    launches the adjoint and only then validates.  (a) same image, gradients within the usual bound of the fp64
+    oracle; (b) with a stale, far too small capacity hint backward raises PairCapacityExceeded BEFORE any gradient
+    reaches a leaf, and train.backward_or_retry renders the camera again -- same gradients as the blocking path."""
+    from oracle import gs_oracle
+    from robosimgs_b200 import GaussianRasterizer, PairCapacityExceeded, _cabi, rasterizer
+    from robosimgs_b200.scenes import settings_from_camera
+    from robosimgs_b200.train import backward_or_retry
+    dev = torch.device("cuda:0")
+    sc, cam, rs_cpu = small_scene(P=30000, degree=1, W=400, H=300)
+    rs = settings_from_camera(cam, 1, bg=(0.2, 0.1, 0.4), device=dev)
+    names = ("means3D", "shs", "opacities", "scales", "rotations")
+    leaves = {k: getattr(sc, k).to(dev).clone().requires_grad_(True) for k in names}
+    m2 = torch.zeros_like(leaves["means3D"], requires_grad=True)
+    w = torch.rand(3, 300, 400, generator=torch.Generator().manual_seed(77))
+    wd = w.to(dev)
+    ref = gs_oracle.backward(_oracle(rs_cpu, sc), w.numpy())
+    r = GaussianRasterizer(rs)
+    frames = []
+
+    def loss_fn():
+        color, _ = r(leaves["means3D"], m2, leaves["opacities"], shs=leaves["shs"], scales=leaves["scales"],
+                     rotations=leaves["rotations"])
+        frames.append(color.detach())
+        return (color * wd).sum()
+
+    def check_grads():
+        for k in names:
+            got = leaves[k].grad.cpu().numpy().reshape(getattr(ref, k).shape)
+            assert max_rel_err(got, getattr(ref, k)) < GRAD_TOL, k
+            leaves[k].grad = None
+    try:
+        _cabi.set_option("bin_shift", 0)
+        rasterizer.ADAPT_BIN_SIZE = False
+        rasterizer._PAIR_HINTS.clear()
+        loss_fn().backward()                                    # blocking path: establishes the hint
+        check_grads()
+        r.defer_pair_check = True
+        loss_fn().backward()                                    # deferred and validated by backward
+        assert r.last_ticket is not None and r.last_ticket.ok() and r.last_ticket.pairs > 40000
+        assert torch.equal(frames[-1], frames[0])
+        check_grads()
+        key = r.last_ticket.hint_key
+        rasterizer._PAIR_HINTS[key] = 16                        # stale hint: the next frame overflows its capacity
+        with pytest.raises(PairCapacityExceeded):
+            loss_fn().backward()
+        assert all(leaves[k].grad is None for k in names)       # nothing reached the leaves
+        assert rasterizer._PAIR_HINTS[key] >= r.last_ticket.pairs
+        rasterizer._PAIR_HINTS[key] = 16
+        n_before = len(frames)
+        backward_or_retry(loss_fn)
+        assert len(frames) == n_before + 2                      # rendered twice: overflow, then complete
+        assert torch.equal(frames[-1], frames[0])
+        check_grads()
+        with torch.no_grad():                                   # no_grad calls stay on the blocking path
+            c, _ = r(leaves["means3D"], m2, leaves["opacities"], shs=leaves["shs"], scales=leaves["scales"],
+                     rotations=leaves["rotations"])
+        assert torch.equal(c, frames[0])
+    finally:
+        _cabi.set_option("bin_shift", -1)
+        rasterizer.ADAPT_BIN_SIZE = True
+
+
 def test_bin_size_policy_follows_the_splat_extent_and_never_changes_results():
     """The Python layer asks for bins of about three splat extents (per-call flags bits 8..11): small splats
     -> finer bins than the image-only default, large splats -> the default or coarser; images, radii and

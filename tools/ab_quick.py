@@ -32,9 +32,10 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(); a.record(); r.fs.fork(); fn(); r.fs.join(); b.record(); torch.cuda.synchronize()
         return a.elapsed_time(b)
+    ONLY_TRAIN = os.environ.get('AB_ONLY', '') == 'train'      # skip the sweep and single-stream passes
     with torch.no_grad():
         sweep(24)
-        sw = [timed(lambda: sweep(K)) / K for _ in range(5)]
+        sw = [timed(lambda: sweep(K)) / K for _ in range(1 if ONLY_TRAIN else 5)]
     m2d = torch.zeros_like(tens["means3D"])
     rs = [settings_from_camera(c, 3, device=dev) for c in cams]
     def single(n):
@@ -43,15 +44,17 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     with torch.no_grad():
         single(10)
         _cabi.profile_enable(True); _cabi.profile_read(True)
-        ss = [timed(lambda: single(K)) / K for _ in range(3)]
+        ss = [timed(lambda: single(K)) / K for _ in range(1 if ONLY_TRAIN else 3)]
         st = _cabi.profile_read(True); _cabi.profile_enable(False)
     leaves = {k: v.clone().requires_grad_(True) for k, v in tens.items()}
     m2 = torch.zeros_like(leaves["means3D"], requires_grad=True)
     target = room_target().to(dev)
+    rast = GaussianRasterizer(rs[0])
+    rast.defer_pair_check = os.environ.get('AB_TRAIN_DEFER', '0') == '1'
     def train(n):
         for s in range(n):
             for v in leaves.values(): v.grad = None
-            c, _ = GaussianRasterizer(rs[0])(leaves["means3D"], m2, leaves["opacities"], shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"])
+            c, _ = rast(leaves["means3D"], m2, leaves["opacities"], shs=leaves["shs"], scales=leaves["scales"], rotations=leaves["rotations"])
             mse_loss(c, target).backward()
     train(8)
     tr = [timed(lambda: train(30)) / 30 for _ in range(5)]
