@@ -275,6 +275,20 @@ int b200gs_context_backward(B200GSContext* ctx, const B200GSParams* prm, int32_t
 int b200gs_context_query(B200GSContext* ctx, int32_t P, int32_t image_height, int32_t image_width,
                          int64_t* tracked_pairs, int32_t* bin_shift);
 
+/*
+ * Captured frames with per-kernel priorities.  `graph` is a cudaGraph_t that holds one captured frame (b200gs_forward
+ * with B200GS_DEFER_PAIR_CHECK, optionally b200gs_export_rgb8 and the caller's copies).  mode 0: plain instantiation.
+ * mode 1: the kernels in front of compositing (projection, bucket scan, pair emission, pair sort) get the device's
+ * highest priority, compositing and the 8-bit export the lowest, and the graph is instantiated with
+ * cudaGraphInstantiateFlagUseNodePriority: with several frames in flight on different streams one frame's short,
+ * latency-bound binning chain runs underneath another frame's compositing instead of queueing behind its CTAs.
+ * mode 2: as 1 with a middle priority for the chain.  Results are identical.  *exec_out is a cudaGraphExec_t;
+ * n_low / n_high (optional) receive the number of kernel nodes marked low / high.
+ */
+int b200gs_graph_instantiate(void* graph, int32_t mode, void** exec_out, int32_t* n_low, int32_t* n_high);
+int b200gs_graph_launch(void* exec, void* stream);
+int b200gs_graph_exec_destroy(void* exec);
+
 /* The two rules of the protocol as pure host functions (no CUDA call; the Python operator layer uses the same):
  *   pair capacity for a tracked pair count D:  D + D/16 + 32768   (0 for D <= 0);
  *   bin shift for a frame that produced D pairs from `touching` visible Gaussians with (16 << used_shift)-px bins:

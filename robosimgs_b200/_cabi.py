@@ -20,6 +20,7 @@ EXPORTED_SYMBOLS = (
     "b200gs_ssim_forward", "b200gs_ssim_backward", "b200gs_adam_step", "b200gs_geom_layout",
     "b200gs_context_create", "b200gs_context_destroy", "b200gs_context_forward", "b200gs_context_ticket_wait",
     "b200gs_context_backward", "b200gs_context_query", "b200gs_policy_pair_capacity", "b200gs_policy_bin_shift",
+    "b200gs_graph_instantiate", "b200gs_graph_launch", "b200gs_graph_exec_destroy",
 )
 ADAM_MAX_GROUPS = 8
 DEFER_PAIR_CHECK = 1
@@ -115,6 +116,12 @@ def lib():
     L.b200gs_policy_pair_capacity.argtypes = [C.c_int64]
     L.b200gs_policy_bin_shift.restype = C.c_int32
     L.b200gs_policy_bin_shift.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_float]
+    L.b200gs_graph_instantiate.restype = C.c_int
+    L.b200gs_graph_instantiate.argtypes = [vp, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.b200gs_graph_launch.restype = C.c_int
+    L.b200gs_graph_launch.argtypes = [vp, vp]
+    L.b200gs_graph_exec_destroy.restype = C.c_int
+    L.b200gs_graph_exec_destroy.argtypes = [vp]
     L.b200gs_context_create.restype = C.c_int
     L.b200gs_context_create.argtypes = [C.POINTER(C.c_void_p)]
     L.b200gs_context_destroy.restype = C.c_int

@@ -12,6 +12,7 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <vector>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -268,6 +269,64 @@ int b200gs_context_backward(B200GSContext* c, const B200GSParams* prm, int32_t u
                          img ? img : c->img.p, num_rendered, dL_dout_color, dL_dmeans3D, dL_dmeans2D, dL_dshs,
                          dL_dcolors_precomp, dL_dopacities, dL_dscales, dL_drotations, dL_dcov3D,
                          B200GSAlloc{&c->scratch, arena_resize}, stream);
+}
+
+// ---- captured frames with per-kernel priorities -----------------------------------------------------------------------
+// A frame is a chain of short, latency-bound kernels (projection, bucket scan, pair emission, pair sort) followed by one
+// long issue-bound kernel (compositing).  When several captured frames are in flight on different streams the block
+// scheduler serves grids in arrival order: the next frame's chain only gets SMs once the compositing grid of the frame
+// in front has placed its last CTA.  Instantiating the frame graph with cudaGraphInstantiateFlagUseNodePriority and
+// marking the chain kernels HIGH, the compositing / export kernels LOW lets a chain run *underneath* another frame's
+// compositing (its CTAs take the slots that compositing CTAs vacate) instead of behind it.
+int b200gs_graph_instantiate(void* graph, int32_t mode, void** exec_out, int32_t* n_low, int32_t* n_high) {
+  if (!graph || !exec_out) { set_error("graph_instantiate: graph/exec_out is NULL"); return B200GS_ERR_INVALID_ARG; }
+  cudaGraph_t g = static_cast<cudaGraph_t>(graph);
+  int lo = 0, hi = 0;
+  int low_count = 0, high_count = 0;
+  int rc;
+  if (mode != 0) {
+    if ((rc = check_cuda(cudaDeviceGetStreamPriorityRange(&lo, &hi), "graph_instantiate: priority range"))) return rc;
+    size_t n = 0;
+    if ((rc = check_cuda(cudaGraphGetNodes(g, nullptr, &n), "graph_instantiate: node count"))) return rc;
+    std::vector<cudaGraphNode_t> nodes(n);
+    if (n && (rc = check_cuda(cudaGraphGetNodes(g, nodes.data(), &n), "graph_instantiate: nodes"))) return rc;
+    for (size_t i = 0; i < n; i++) {
+      cudaGraphNodeType ty;
+      if ((rc = check_cuda(cudaGraphNodeGetType(nodes[i], &ty), "graph_instantiate: node type"))) return rc;
+      if (ty != cudaGraphNodeTypeKernel) continue;
+      cudaKernelNodeParams kp;
+      if ((rc = check_cuda(cudaGraphKernelNodeGetParams(nodes[i], &kp), "graph_instantiate: kernel params"))) return rc;
+      const char* name = nullptr;
+      if (cudaFuncGetName(&name, kp.func) != cudaSuccess) { cudaGetLastError(); name = nullptr; }
+      // compositing (k_render_fwd*) and the 8-bit export run LOW; everything in front of them HIGH
+      const bool low = name && (strstr(name, "k_render_fwd") || strstr(name, "k_export_rgb8"));
+      cudaKernelNodeAttrValue v;
+      memset(&v, 0, sizeof(v));
+      v.priority = low ? lo : (mode == 2 ? (lo + hi) / 2 : hi);
+      if ((rc = check_cuda(cudaGraphKernelNodeSetAttribute(nodes[i], cudaKernelNodeAttributePriority, &v),
+                           "graph_instantiate: set priority")))
+        return rc;
+      (low ? low_count : high_count)++;
+    }
+  }
+  cudaGraphExec_t ex = nullptr;
+  if ((rc = check_cuda(cudaGraphInstantiateWithFlags(&ex, g, mode != 0 ? cudaGraphInstantiateFlagUseNodePriority : 0),
+                       "graph_instantiate")))
+    return rc;
+  *exec_out = ex;
+  if (n_low) *n_low = low_count;
+  if (n_high) *n_high = high_count;
+  return 0;
+}
+
+int b200gs_graph_launch(void* exec, void* stream) {
+  if (!exec) { set_error("graph_launch: exec is NULL"); return B200GS_ERR_INVALID_ARG; }
+  return check_cuda(cudaGraphLaunch(static_cast<cudaGraphExec_t>(exec), static_cast<cudaStream_t>(stream)), "graph_launch");
+}
+
+int b200gs_graph_exec_destroy(void* exec) {
+  if (!exec) return 0;
+  return check_cuda(cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(exec)), "graph_exec_destroy");
 }
 
 }  // extern "C"

@@ -38,9 +38,9 @@ namespace b200gs {
 #define PROJECT_BWD_EARLY_CLAMP 0  // 0.1065 -> 0.111 without (256-thread CTAs)
 #endif
 // CTA size of the projection adjoint (its SH-gradient slab is THREADS x M x 12 bytes and leaves behind ONE barrier):
-// 256 threads 0.1065 ms, 128 threads 0.0999 (same 24 warps per SM; the warps of a CTA wait for its slowest one)
+// 256 threads 0.1054 ms, 128: 0.0994, 64: 0.0968, 32: 0.0967 (same 24 warps per SM; the warps of a CTA wait for its slowest)
 #ifndef PROJECT_BWD_THREADS
-#define PROJECT_BWD_THREADS 128
+#define PROJECT_BWD_THREADS 64
 #endif
 #ifndef PROJECT_BWD_MIN_BLOCKS
 #define PROJECT_BWD_MIN_BLOCKS (768 / PROJECT_BWD_THREADS)

@@ -6,13 +6,17 @@ reference's (unreleased) per-frame scene renderer (/root/reference/README.md:29,
 """
 from __future__ import annotations
 
+import ctypes as C
 import os
 from typing import Callable, List, Optional, Sequence
 
 import torch
 import torch.distributed as dist
 
+from . import _cabi
 from .cameras import Camera
+
+NODE_PRIORITY = 0      # default of SceneRenderer(node_priority=None); see b200gs_graph_instantiate
 
 SCENE_FIELDS = ("means3D", "shs", "opacities", "scales", "rotations")
 
@@ -146,9 +150,16 @@ class SceneRenderer:
     _tags = 0
 
     def __init__(self, scene: dict, sh_degree: int, bg: torch.Tensor, height: int, width: int, streams: int = 2,
-                 graphs: bool = True, host_frames: bool = True):
+                 graphs: bool = True, host_frames: bool = True, node_priority: Optional[int] = None):
         from . import rasterizer
         self.rz = rasterizer
+        # node_priority (0 off, 1 / 2: b200gs_graph_instantiate modes): the captured frame is instantiated by the library
+        # with per-kernel priorities -- binning chain high, compositing low -- so that the chains of the frames in
+        # flight run underneath each other's compositing.  Default: environment B200GS_NODE_PRIORITY, else NODE_PRIORITY.
+        if node_priority is None:
+            node_priority = int(os.environ.get("B200GS_NODE_PRIORITY", NODE_PRIORITY))
+        self.node_priority = int(node_priority) if graphs else 0
+        self.priority_nodes = (0, 0)      # (low, high) kernel nodes of the last instantiated frame graph
         self.scene, self.deg, self.H, self.W = scene, int(sh_degree), int(height), int(width)
         self.dev = scene["means3D"].device
         self.bg = bg.to(self.dev)
@@ -234,12 +245,23 @@ class SceneRenderer:
                 if slot["graph"] is None or slot["graph_capacity"] != self.capacity or slot.get("tf") != tf:
                     self._enqueue(slot, *tf, exact=False, in_capture=False)       # sizes this slot's private scratch
                     slot["stream"].synchronize()
-                    g = torch.cuda.CUDAGraph()
+                    g = torch.cuda.CUDAGraph(keep_graph=True) if self.node_priority else torch.cuda.CUDAGraph()
                     # thread_local: other threads (e.g. the NCCL watchdog of a multi-GPU sweep) may keep calling CUDA
                     with torch.cuda.graph(g, stream=slot["stream"], capture_error_mode="thread_local"):
                         self._enqueue(slot, *tf, exact=False, in_capture=True)
+                    self._drop_exec(slot)
+                    if self.node_priority:
+                        # torch owns the captured graph and its memory pool; the library instantiates it
+                        ex, lo, hi = C.c_void_p(), C.c_int32(0), C.c_int32(0)
+                        _cabi.check(_cabi.lib().b200gs_graph_instantiate(C.c_void_p(int(g.raw_cuda_graph())),
+                                                                        C.c_int32(self.node_priority), C.byref(ex),
+                                                                        C.byref(lo), C.byref(hi)))
+                        slot["exec"], self.priority_nodes = ex, (lo.value, hi.value)
                     slot["graph"], slot["graph_capacity"], slot["tf"] = g, self.capacity, tf
-                slot["graph"].replay()
+                if slot.get("exec") is not None:
+                    _cabi.check(_cabi.lib().b200gs_graph_launch(slot["exec"], C.c_void_p(slot["stream"].cuda_stream)))
+                else:
+                    slot["graph"].replay()
                 key = (self.dev.index, self.scene["means3D"].shape[0], self.H, self.W)
                 slot["ticket"] = self.rz.PairTicket(self.capacity, key, slot["word"])
             else:
@@ -269,6 +291,22 @@ class SceneRenderer:
 
     def in_flight_limit(self) -> int:
         return len(self.slots)
+
+    def _drop_exec(self, slot) -> None:
+        ex = slot.pop("exec", None)
+        if ex is not None:
+            slot["stream"].synchronize()
+            _cabi.lib().b200gs_graph_exec_destroy(ex)
+
+    def close(self) -> None:
+        for slot in self.slots:
+            self._drop_exec(slot)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def render_sweep(cameras: Sequence[Camera], render_fn: Callable[[Camera], torch.Tensor],

@@ -110,11 +110,14 @@ def test_fused_photometric_loss_matches_torch():
         assert torch.allclose(g1, g2, rtol=1e-5, atol=1e-9)
 
 
-@pytest.mark.parametrize("graphs", [True, False])
+@pytest.mark.parametrize("graphs", [True, False, "node-priority"])
 def test_scene_renderer_host_frames_match_plain_path(graphs):
     """sweep.SceneRenderer (host camera in, pinned 8-bit frame out, deferred pair check, one CUDA graph
     per frame slot) returns exactly the frames of forward + export_rgb8, also across a view change that
-    overflows the captured pair capacity (frame rendered again, graphs re-captured)."""
+    overflows the captured pair capacity (frame rendered again, graphs re-captured).  "node-priority": the frame
+    graphs are instantiated by the library (b200gs_graph_instantiate: binning chain high, compositing low)."""
+    prio = 1 if graphs == "node-priority" else 0
+    graphs = bool(graphs)
     from robosimgs_b200 import GaussianRasterizer, export_rgb8
     from robosimgs_b200.cameras import camera_look_at, orbit_cameras
     from robosimgs_b200.scenes import cube_scene, settings_from_camera
@@ -129,7 +132,7 @@ def test_scene_renderer_host_frames_match_plain_path(graphs):
     from robosimgs_b200 import _cabi
     _cabi.set_option("bin_shift", 0)           # 16-px bins: the near view has several times the pairs of the far ones
     try:
-        r = SceneRenderer(scene, 1, bg, 240, 320, streams=2, graphs=graphs)
+        r = SceneRenderer(scene, 1, bg, 240, 320, streams=2, graphs=graphs, node_priority=prio)
         m2 = torch.zeros_like(scene["means3D"])
         got, handles = [], []
         for cam in cams:
@@ -141,6 +144,9 @@ def test_scene_renderer_host_frames_match_plain_path(graphs):
     finally:
         _cabi.set_option("bin_shift", -1)
     assert r.redone >= 1                       # the jump to the near camera overflowed the capacity
+    if prio:
+        assert r.priority_nodes[0] == 2 and r.priority_nodes[1] >= 4      # compositing + export low, the chain high
+        r.close()
     with torch.no_grad():
         for cam, frame in zip(cams, got):
             rs = settings_from_camera(cam, 1, bg=(0.1, 0.2, 0.3), device=dev)

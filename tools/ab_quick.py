@@ -63,7 +63,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     st2 = _cabi.profile_read(True); _cabi.profile_enable(False)
     st.update({k: v for k, v in st2.items() if k in ("render_bwd", "project_bwd")})
     print(json.dumps({"sweep_ms": round(statistics.median(sw), 4), "sweep_runs": [round(x, 4) for x in sw], "single_ms": round(statistics.median(ss), 4),
-                      "train_ms": round(statistics.median(tr), 4), "train_runs": [round(x, 4) for x in tr], "redone": r.redone,
+                      "train_ms": round(statistics.median(tr), 4), "train_runs": [round(x, 4) for x in tr], "redone": r.redone, "prio_nodes": list(r.priority_nodes),
                       "stages": {k: round(v[0] / max(v[1], 1), 4) for k, v in st.items() if v[1]}}))
     sys.exit(0)
 
