@@ -49,6 +49,7 @@ extern "C" {
  */
 #define B200GS_DEFER_PAIR_CHECK 1
 #define B200GS_FORWARD_ONLY 2
+#define B200GS_OUT_RGB8 4
 #define B200GS_BIN_SHIFT_HINT(s) (((s) + 1) << 8)
 
 typedef struct B200GSParams {
@@ -71,6 +72,10 @@ typedef struct B200GSParams {
                              bit 1 (B200GS_FORWARD_ONLY): no backward pass will follow this frame -- the per-pixel state
                              the adjoint replays from (accumulated colour, final transmittance, list position: 20
                              bytes per pixel of `img`) is not written; out_color and radii are unchanged.
+                             bit 2 (B200GS_OUT_RGB8): `out_color` points to H*W*3 BYTES and receives the frame as
+                             [H][W][3] 8-bit RGB (clamp to [0,1], round to nearest -- what b200gs_export_rgb8 makes of the
+                             fp32 frame, bit for bit) straight from the compositing kernel: a datagen sweep neither
+                             writes nor re-reads the 12-byte-per-pixel fp32 frame.
                              bits 8..11 (B200GS_BIN_SHIFT_HINT(s) = (s + 1) << 8, 0 = none): pairs are binned per
                              (16 << s)^2 pixels for this call instead of the automatic choice -- a performance hint
                              (results are identical for every bin size); b200gs_backward must get the same bits. */

@@ -25,6 +25,7 @@ EXPORTED_SYMBOLS = (
 ADAM_MAX_GROUPS = 8
 DEFER_PAIR_CHECK = 1
 FORWARD_ONLY = 2
+OUT_RGB8 = 4
 NUM_STAGES = 8
 
 

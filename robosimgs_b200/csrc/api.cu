@@ -634,6 +634,7 @@ int b200gs_forward(const B200GSParams* prm, const float* bg, const float* viewma
     const bool fwd_only = (prm->flags & B200GS_FORWARD_ONLY) != 0;     // nothing is kept for the adjoint
     ra.pix = fwd_only ? nullptr : ib.pix; ra.n_contrib = fwd_only ? nullptr : ib.n_contrib;
     ra.vec4 = ((W & 3) == 0 && (reinterpret_cast<uintptr_t>(out_color) & 15) == 0) ? 1 : 0;
+    ra.out_rgb8 = (prm->flags & B200GS_OUT_RGB8) ? reinterpret_cast<uint8_t*>(out_color) : nullptr;
     {
       StageTimer t(5, st);
       if (use_render4(gx * gy)) launch_render4(ra, st);

@@ -171,7 +171,7 @@ int b200gs_context_forward(B200GSContext* c, const B200GSParams* prm, const floa
   const int used_shift = pol.shift >= 0 ? pol.shift : default_bin_shift(prm->image_height, prm->image_width);
   B200GSParams p2 = *prm;
   p2.pair_capacity_hint = hint;
-  p2.flags = (pol.shift >= 0 ? B200GS_BIN_SHIFT_HINT(pol.shift) : 0) | (prm->flags & B200GS_FORWARD_ONLY);
+  p2.flags = (pol.shift >= 0 ? B200GS_BIN_SHIFT_HINT(pol.shift) : 0) | (prm->flags & (B200GS_FORWARD_ONLY | B200GS_OUT_RGB8));
   *used_flags = p2.flags;
   *ticket = -1;
   for (Arena* a : {&c->geom, &c->binning, &c->img}) a->stream = st;

@@ -106,9 +106,13 @@ struct RenderArgs {
   const float4* slab;          // [D] records in list order (written by the bucket sort) or nullptr: TMA-fed ring
   const float* bg;
   float* out_color;     // [3][H][W]
+  uint8_t* out_rgb8;    // not null: the frame leaves as [H][W][3] 8-bit RGB instead (B200GS_OUT_RGB8), out_color unused
   float4* pix;          // [H*W]
   uint32_t* n_contrib;  // [H*W]
 };
+
+// fp32 colour -> 8-bit channel, the conversion of k_export_rgb8 (clamp to [0,1], round to nearest)
+__device__ __forceinline__ uint32_t rgb8_of(float v) { return (uint32_t)__float2int_rn(__saturatef(v) * 255.f); }
 
 struct RenderBwdArgs {
   int W, H, gbx, bin_shift;

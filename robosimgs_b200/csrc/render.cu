@@ -229,9 +229,16 @@ __global__ void __launch_bounds__(256) k_render_fwd(RenderArgs a) {
       a.pix[pid] = make_float4(Cr, Cg, Cb, T);
       a.n_contrib[pid] = last;
     }
-    a.out_color[pid] = __fmaf_rn(T, __ldg(a.bg + 0), Cr);
-    a.out_color[hw + pid] = __fmaf_rn(T, __ldg(a.bg + 1), Cg);
-    a.out_color[2 * hw + pid] = __fmaf_rn(T, __ldg(a.bg + 2), Cb);
+    const float o0 = __fmaf_rn(T, __ldg(a.bg + 0), Cr), o1 = __fmaf_rn(T, __ldg(a.bg + 1), Cg);
+    const float o2 = __fmaf_rn(T, __ldg(a.bg + 2), Cb);
+    if (a.out_rgb8) {
+      uint8_t* o = a.out_rgb8 + pid * 3;
+      o[0] = (uint8_t)rgb8_of(o0); o[1] = (uint8_t)rgb8_of(o1); o[2] = (uint8_t)rgb8_of(o2);
+    } else {
+      a.out_color[pid] = o0;
+      a.out_color[hw + pid] = o1;
+      a.out_color[2 * hw + pid] = o2;
+    }
   }
 }
 
@@ -393,7 +400,7 @@ __global__ void __launch_bounds__(256) k_export_rgb8(const float* __restrict__ c
   const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // group of 4 pixels
   const size_t p0 = q * 4;
   if (p0 >= npx) return;
-  auto cvt = [](float v) { return (uint32_t)__float2int_rn(__saturatef(v) * 255.f); };
+  auto cvt = [](float v) { return rgb8_of(v); };
   if (p0 + 3 < npx && (npx & 3) == 0) {
     const float4 r = *reinterpret_cast<const float4*>(color + p0);
     const float4 g = *reinterpret_cast<const float4*>(color + npx + p0);

@@ -254,6 +254,20 @@ __global__ void __launch_bounds__(R4_THREADS, R4_FWD_MINB) k_render_fwd4(RenderA
       *reinterpret_cast<uint4*>(a.n_contrib + pid) = make_uint4(nstop[0], nstop[1], nstop[2], nstop[3]);
     }
     const float b0 = __ldg(a.bg + 0), b1 = __ldg(a.bg + 1), b2 = __ldg(a.bg + 2);
+    if (a.out_rgb8) {
+      // the thread's four pixels are 12 contiguous bytes of the [H][W][3] frame: three aligned 32-bit words
+      uint32_t c[12];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        c[3 * i + 0] = rgb8_of(__fmaf_rn(Tf[i], b0, R_[i]));
+        c[3 * i + 1] = rgb8_of(__fmaf_rn(Tf[i], b1, G_[i]));
+        c[3 * i + 2] = rgb8_of(__fmaf_rn(Tf[i], b2, B_[i]));
+      }
+      uint32_t* o = reinterpret_cast<uint32_t*>(a.out_rgb8 + pid * 3);
+#pragma unroll
+      for (int w = 0; w < 3; w++) o[w] = c[4 * w] | (c[4 * w + 1] << 8) | (c[4 * w + 2] << 16) | (c[4 * w + 3] << 24);
+      return;
+    }
     *reinterpret_cast<float4*>(a.out_color + pid) =
         make_float4(__fmaf_rn(Tf[0], b0, R_[0]), __fmaf_rn(Tf[1], b0, R_[1]), __fmaf_rn(Tf[2], b0, R_[2]),
                     __fmaf_rn(Tf[3], b0, R_[3]));
@@ -271,9 +285,16 @@ __global__ void __launch_bounds__(R4_THREADS, R4_FWD_MINB) k_render_fwd4(RenderA
         a.pix[pid + i] = make_float4(R_[i], G_[i], B_[i], Tf[i]);
         a.n_contrib[pid + i] = nstop[i];
       }
-      a.out_color[pid + i] = __fmaf_rn(Tf[i], __ldg(a.bg + 0), R_[i]);
-      a.out_color[hw + pid + i] = __fmaf_rn(Tf[i], __ldg(a.bg + 1), G_[i]);
-      a.out_color[2 * hw + pid + i] = __fmaf_rn(Tf[i], __ldg(a.bg + 2), B_[i]);
+      const float o0 = __fmaf_rn(Tf[i], __ldg(a.bg + 0), R_[i]), o1 = __fmaf_rn(Tf[i], __ldg(a.bg + 1), G_[i]);
+      const float o2 = __fmaf_rn(Tf[i], __ldg(a.bg + 2), B_[i]);
+      if (a.out_rgb8) {
+        uint8_t* o = a.out_rgb8 + (pid + i) * 3;
+        o[0] = (uint8_t)rgb8_of(o0); o[1] = (uint8_t)rgb8_of(o1); o[2] = (uint8_t)rgb8_of(o2);
+        continue;
+      }
+      a.out_color[pid + i] = o0;
+      a.out_color[hw + pid + i] = o1;
+      a.out_color[2 * hw + pid + i] = o2;
     }
   }
 }

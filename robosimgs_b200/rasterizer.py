@@ -243,10 +243,13 @@ class DeferOptions(list):
     word that receives the pair count; record_event -- False inside stream capture (the caller records
     its own event after replaying the graph)."""
 
-    def __init__(self, capacity: int = 0, word=None, record_event: bool = True, train: bool = False):
+    def __init__(self, capacity: int = 0, word=None, record_event: bool = True, train: bool = False, rgb8=None):
         super().__init__()
         self.capacity, self.word, self.record_event = int(capacity), word, bool(record_event)
         self.train = bool(train)      # the frame keeps its adjoint state; backward validates the ticket
+        # rgb8: CUDA uint8 tensor [H, W, 3] -- the compositing kernel writes the finished 8-bit frame straight into it
+        # (B200GS_OUT_RGB8; bit-identical to export_rgb8 of the fp32 frame) and the call returns it as `color`
+        self.rgb8 = rgb8
 
 
 class PairCapacityExceeded(_cabi.B200GSError):
@@ -301,8 +304,15 @@ class _RasterizeGaussians(torch.autograd.Function):
         # written unless the caller wants the alpha channel, which is read from it
         keep_state = want_alpha or (ticket_box is not None and opts.train)
         fwd_flags = ((_cabi.DEFER_PAIR_CHECK | (0 if keep_state else _cabi.FORWARD_ONLY)) if defer else 0)
+        rgb8 = opts.rgb8 if ticket_box is not None else None
+        if rgb8 is not None:
+            if rgb8.dtype != torch.uint8 or tuple(rgb8.shape) != (H, W, 3) or rgb8.device != dev or not rgb8.is_contiguous():
+                raise _cabi.B200GSError("rgb8 output must be a contiguous CUDA uint8 tensor of shape [H, W, 3]")
+            if opts.train:
+                raise _cabi.B200GSError("an 8-bit frame carries no gradient: rgb8 output is for forward-only rendering")
+            fwd_flags |= _cabi.OUT_RGB8
         prm = _params(P, M, rs, hint, near_plane, fwd_flags | bin_flags)
-        color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+        color = rgb8 if rgb8 is not None else torch.empty((3, H, W), dtype=torch.float32, device=dev)
         radii = torch.empty((P,), dtype=torch.int32, device=dev)
         num_rendered = C.c_int32(0)
         nr_ptr = C.c_void_p(ticket.word.data_ptr()) if defer else C.cast(C.pointer(num_rendered), C.c_void_p)

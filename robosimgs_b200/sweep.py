@@ -16,6 +16,7 @@ import torch.distributed as dist
 from . import _cabi
 from .cameras import Camera
 
+FUSED_RGB8 = os.environ.get("B200GS_FUSED_RGB8", "1") != "0"     # host-frame path: 8-bit frame from the compositing kernel
 NODE_PRIORITY = 0      # default of SceneRenderer(node_priority=None); see b200gs_graph_instantiate
 
 SCENE_FIELDS = ("means3D", "shs", "opacities", "scales", "rotations")
@@ -196,9 +197,11 @@ class SceneRenderer:
         if exact or self.capacity <= 0:
             color, _ = r(sc["means3D"], self.means2D, sc["opacities"], **kw)
         else:
-            opts = rz.DeferOptions(capacity=self.capacity, word=slot["word"], record_event=False)
+            # host frames: the compositing kernel writes the 8-bit frame itself (no fp32 frame, no export pass)
+            opts = rz.DeferOptions(capacity=self.capacity, word=slot["word"], record_event=False,
+                                   rgb8=slot["rgb8"] if (self.host_frames and FUSED_RGB8) else None)
             color, _, ticket = r.forward_deferred(sc["means3D"], self.means2D, sc["opacities"], options=opts, **kw)
-        if self.host_frames:
+        if self.host_frames and color.dtype != torch.uint8:        # (the exact path renders fp32)
             rz.export_rgb8(color, out=slot["rgb8"])
         if self.host_frames:
             slot["frame_host"].copy_(slot["rgb8"], non_blocking=True)

@@ -288,6 +288,38 @@ def test_deferred_pair_check_ticket_protocol():
         rasterizer.ADAPT_BIN_SIZE = True
 
 
+@pytest.mark.parametrize("W,H", [(1280, 1024), (1282, 1022), (200, 120), (201, 119)])
+def test_fused_rgb8_frame_equals_export_of_the_fp32_frame(W, H):
+    """B200GS_OUT_RGB8: the compositing kernel writes the [H][W][3] 8-bit frame itself -- bit for bit what
+    b200gs_export_rgb8 makes of the fp32 frame.  Both compositing kernels (four pixels per thread from 4096 tiles up,
+    one pixel per thread below), with and without the 128-bit path (W % 4), synchronous (no hint yet) and deferred."""
+    from robosimgs_b200 import GaussianRasterizer, export_rgb8, rasterizer
+    from robosimgs_b200.scenes import settings_from_camera
+    dev = torch.device("cuda:0")
+    sc, cam, _ = small_scene(P=6000, degree=2, W=W, H=H)
+    rs = settings_from_camera(cam, 2, bg=(0.2, 0.6, 0.4), device=dev)
+    t = {k: getattr(sc, k).to(dev) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+    m2 = torch.zeros_like(t["means3D"])
+    kw = dict(shs=t["shs"], scales=t["scales"], rotations=t["rotations"])
+    with torch.no_grad():
+        r = GaussianRasterizer(rs)
+        rasterizer._PAIR_HINTS.clear()
+        ref, rref = r(t["means3D"], m2, t["opacities"], **kw)
+        want = export_rgb8(ref)
+        assert want.float().std() > 10                           # a real picture, not a constant
+        rasterizer._PAIR_HINTS.clear()
+        for attempt in range(2):                                 # first call: exact path; second: deferred
+            out = torch.full((H, W, 3), 77, dtype=torch.uint8, device=dev)
+            got, radii, ticket = r.forward_deferred(t["means3D"], m2, t["opacities"],
+                                                    options=rasterizer.DeferOptions(rgb8=out), **kw)
+            assert ticket.ok() and (ticket.hint > 0) == (attempt == 1)
+            assert got.dtype == torch.uint8 and got.data_ptr() == out.data_ptr()
+            assert torch.equal(out, want) and torch.equal(radii, rref)
+        with pytest.raises(Exception, match="rgb8"):
+            r.forward_deferred(t["means3D"], m2, t["opacities"],
+                               options=rasterizer.DeferOptions(rgb8=torch.empty((H, W, 4), dtype=torch.uint8, device=dev)), **kw)
+
+
 def test_training_step_with_deferred_pair_check_matches_oracle_and_recovers_from_overflow():
     """GaussianRasterizer.defer_pair_check (opt-in): forward returns without waiting for the pair count, backward
     launches the adjoint and only then validates.  (a) same image, gradients within the usual bound of the fp64

@@ -145,7 +145,7 @@ def test_scene_renderer_host_frames_match_plain_path(graphs):
         _cabi.set_option("bin_shift", -1)
     assert r.redone >= 1                       # the jump to the near camera overflowed the capacity
     if prio:
-        assert r.priority_nodes[0] == 2 and r.priority_nodes[1] >= 4      # compositing + export low, the chain high
+        assert r.priority_nodes[0] >= 1 and r.priority_nodes[1] >= 4      # compositing low, the chain high
         r.close()
     with torch.no_grad():
         for cam, frame in zip(cams, got):

@@ -36,6 +36,26 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     with torch.no_grad():
         sweep(24)
         sw = [timed(lambda: sweep(K)) / K for _ in range(1 if ONLY_TRAIN else 5)]
+    # host-frame path (bench.py's e2e): camera from pinned host memory in, 8-bit frame in pinned host memory out
+    e2e = []
+    if not ONLY_TRAIN:
+        rh = SceneRenderer(tens, 3, bg, 1080, 1920, streams=int(os.environ.get('AB_E2E_STREAMS', '6')), graphs=True, host_frames=True)
+        ph = []
+        def sweep_h(n):
+            for s in range(n):
+                while len(ph) >= rh.in_flight_limit():
+                    rh.collect(ph.pop(0))
+                ph.append(rh.submit(cams[s % len(cams)]))
+            while ph:
+                rh.collect(ph.pop(0))
+        def timed_h(fn):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); a.record(); rh.fs.fork(); fn(); rh.fs.join(); b.record(); torch.cuda.synchronize()
+            return a.elapsed_time(b)
+        with torch.no_grad():
+            sweep_h(36)
+            e2e = [round(timed_h(lambda: sweep_h(K)) / K, 4) for _ in range(5)]
+        rh.close(); del rh
     m2d = torch.zeros_like(tens["means3D"])
     rs = [settings_from_camera(c, 3, device=dev) for c in cams]
     def single(n):
@@ -63,7 +83,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     st2 = _cabi.profile_read(True); _cabi.profile_enable(False)
     st.update({k: v for k, v in st2.items() if k in ("render_bwd", "project_bwd")})
     print(json.dumps({"sweep_ms": round(statistics.median(sw), 4), "sweep_runs": [round(x, 4) for x in sw], "single_ms": round(statistics.median(ss), 4),
-                      "train_ms": round(statistics.median(tr), 4), "train_runs": [round(x, 4) for x in tr], "redone": r.redone, "prio_nodes": list(r.priority_nodes),
+                      "e2e_ms": (statistics.median(e2e) if e2e else None), "train_ms": round(statistics.median(tr), 4), "train_runs": [round(x, 4) for x in tr], "redone": r.redone, "prio_nodes": list(r.priority_nodes),
                       "stages": {k: round(v[0] / max(v[1], 1), 4) for k, v in st.items() if v[1]}}))
     sys.exit(0)
 
