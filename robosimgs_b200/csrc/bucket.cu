@@ -38,6 +38,15 @@
 #include "spans.cuh"
 #include "binsort.cuh"
 
+// CTAs of the one-CTA-per-fat-segment kernel (persistent over the queue).  A CTA needs a whole SM's register file (512
+// threads x 128 registers), so each one waits for an SM to drain -- also when the queue is empty.
+#ifndef BUCKET_SORT_BIG_CTAS
+#define BUCKET_SORT_BIG_CTAS (148 * 2)
+#endif
+#ifndef BUCKET_SORT_BIG_SKIP      // measurement only: never launch it (wrong on scenes with fat segments)
+#define BUCKET_SORT_BIG_SKIP 0
+#endif
+
 namespace b200gs {
 
 // ---- k_bucket_scan --------------------------------------------------------------------------------
@@ -548,7 +557,9 @@ void launch_bucket_sort(const BucketArgs& a, cudaStream_t st) {
   if (a.P == 0 || a.capacity == 0) return;
   const uint32_t max_windows = a.capacity / BUCKET_WINDOW + a.num_bins;     // sum over bins of ceil(pairs / W)
   k_bucket_sort<<<(max_windows + SORT_WARPS - 1) / SORT_WARPS, 32 * SORT_WARPS, 0, st>>>(a);
-  k_bucket_sort_big<<<148 * 2, BS_THREADS, 0, st>>>(a);
+#if !BUCKET_SORT_BIG_SKIP
+  k_bucket_sort_big<<<BUCKET_SORT_BIG_CTAS, BS_THREADS, 0, st>>>(a);
+#endif
   count_launch(2);
 }
 

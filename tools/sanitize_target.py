@@ -54,3 +54,23 @@ gs_loss(x, torch.rand(3, 45, 70, device=dev)).backward()
 opt = FusedAdam([x], lr=1e-2); opt.step()
 torch.cuda.synchronize()
 print("ok train neighbours", float(x.mean()))
+# forward-only frames (B200GS_FORWARD_ONLY) with the 8-bit frame written by the compositing kernel (B200GS_OUT_RGB8):
+# ragged widths (scalar epilogue) and multiples of 4 (packed words), both compositing kernel families
+from robosimgs_b200 import GaussianRasterizer, rasterizer
+from robosimgs_b200.scenes import settings_from_camera
+for render in (0, 1):
+    _cabi.set_option("render", render)
+    for (W, H) in ((200, 120), (201, 119)):
+        sc, cam, _ = small_scene(P=3000, degree=2, W=W, H=H)
+        rs = settings_from_camera(cam, 2, bg=(0.2, 0.6, 0.4), device=dev)
+        t = {k: getattr(sc, k).to(dev) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+        rasterizer._PAIR_HINTS.clear()
+        with torch.no_grad():
+            for attempt in range(2):
+                out = torch.zeros((H, W, 3), dtype=torch.uint8, device=dev)
+                got, _, ticket = GaussianRasterizer(rs).forward_deferred(
+                    t["means3D"], torch.zeros_like(t["means3D"]), t["opacities"], shs=t["shs"], scales=t["scales"],
+                    rotations=t["rotations"], options=rasterizer.DeferOptions(rgb8=out))
+                assert ticket.ok()
+        print("ok rgb8", render, W, H, float(out.float().mean()), flush=True)
+_cabi.set_option("render", -1)
