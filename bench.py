@@ -491,7 +491,7 @@ def run_b200(args):
                                      "running (max over ranks, same timing harness): the rate this box absorbs",
                 "cuda_graphs": not args.no_graphs,
                 "what": "robosimgs_b200.sweep.SceneRenderer.submit/collect per frame: camera (view, proj, campos) from "
-                        "pinned host memory, forward with deferred pair check + export_rgb8, finished 8-bit RGB frame "
+                        "pinned host memory, forward with deferred pair check writing the 8-bit RGB frame from the compositing kernel (B200GS_OUT_RGB8), finished frame "
                         "copied to pinned host memory and collected by the consumer; one captured CUDA graph per frame "
                         "slot, consecutive frames alternate streams; scene resident in HBM as in the reference's render loop"},
         "gpu_launches": launches,
