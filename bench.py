@@ -435,6 +435,7 @@ def run_b200(args):
         except Exception:
             traffic_tab = {}
     traffic = traffic_tab.get(dom)
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
     kernels = []
     for k, v in {**st_ms, **st_ms_train}.items():
         row = {"stage": k, "ms": round(v, 5), "algorithmic_bytes": per_stage_bytes[k],
@@ -444,6 +445,12 @@ def run_b200(args):
             row["dram_bytes"] = traffic_tab[k]
             row["dram_GBps"] = round(traffic_tab[k] / (v * 1e-3) / 1e9, 1)
             row["dram_frac"] = round(traffic_tab[k] / (v * 1e-3) / 1e9 / peak, 4)
+        wi = (traffic_tab.get("_warp_instructions") or {}).get(k)
+        if isinstance(wi, (int, float)) and sm_count and clocks.get("sm_mhz"):
+            # issue-slot view of the same launch (static instruction count from the committed ncu capture, like the
+            # DRAM bytes): warp instructions / (SMs x 4 schedulers x SM clock x event-timed duration)
+            row["warp_instructions"] = int(wi)
+            row["issue_frac"] = round(wi / (sm_count * 4 * clocks["sm_mhz"] * 1e6 * v * 1e-3), 4)
         kernels.append(row)
     out = {
         "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": K, "warmup": Wm,
@@ -498,6 +505,9 @@ def run_b200(args):
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": dom_gbs, "peak": peak, "unit": "GB/s",
                      "frac": dom_gbs / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "kernels": kernels,
+                     "bound_note": "the contract's two bounds are hbm | tensor; the dominant kernel (compositing) is neither: "
+                                   "it is bound by FP32 instruction issue and dependent-instruction latency -- "
+                                   "kernels[].issue_frac gives the share of the GPU's issue slots each launch used",
                      "algorithmic_bytes_per_launch": per_stage_bytes[dom], "ms_per_launch": st_ms[dom],
                      "frame_fwd": {"bytes": bytes_fwd, "GBps": bytes_fwd / (fwd_ms / K * 1e-3) / 1e9,
                                    "frac": bytes_fwd / (fwd_ms / K * 1e-3) / 1e9 / peak,
