@@ -255,7 +255,7 @@ class DeferOptions(list):
 class PairCapacityExceeded(_cabi.B200GSError):
     """A training step made with ``GaussianRasterizer.defer_pair_check`` produced more pairs than the speculative
     capacity: the frame the loss saw was incomplete and so are the gradients.  The capacity hint has been raised;
-    run the step again (robosimgs_b200.train.render_step does)."""
+    run the step again (robosimgs_b200.train.backward_or_retry does)."""
 
 
 class _RasterizeGaussians(torch.autograd.Function):
