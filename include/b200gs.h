@@ -266,7 +266,10 @@ int b200gs_context_forward(B200GSContext* ctx, const B200GSParams* prm, const fl
 int b200gs_context_ticket_wait(B200GSContext* ctx, int64_t ticket, int32_t* num_rendered, int32_t* complete);
 
 /* Backward for the LAST b200gs_context_forward of this context that used the context's own arenas (NULL geom /
- * binning / img select them); otherwise identical to b200gs_backward.  used_flags: from that forward call. */
+ * binning / img select them); otherwise identical to b200gs_backward.  used_flags: from that forward call.
+ * After a DEFERRED forward (whose pair count the host does not know yet) pass any positive num_rendered -- the adjoint
+ * only needs to know that there are pairs -- and validate the ticket afterwards (b200gs_context_ticket_wait): a training
+ * step then never waits inside the step; if the ticket reports an incomplete frame, discard the gradients and repeat it. */
 int b200gs_context_backward(B200GSContext* ctx, const B200GSParams* prm, int32_t used_flags, const float* bg,
                             const float* viewmatrix, const float* projmatrix, const float* campos,
                             const float* means3D, const float* shs, const float* colors_precomp,

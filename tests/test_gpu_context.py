@@ -158,6 +158,25 @@ def test_context_backward_matches_oracle_and_bin_policy_never_changes_results():
             r = getattr(ref, k)
             assert max_rel_err(g[k].cpu().numpy().reshape(r.shape), r) < 1e-3, k
         assert max_rel_err(g2d.cpu().numpy(), ref.means2D) < 1e-3
+        # training without a host wait, C side: deferred forward (adjoint state kept), backward launched at once with any
+        # positive num_rendered (the adjoint only needs to know that there are pairs), THEN the ticket is validated
+        g_def = {k: torch.empty_like(v) for k, v in dsc.items()}
+        g2d_def = torch.empty(P, 3, device="cuda")
+        color3, radii3, _, ticket3, flags3, prm3 = ctx.forward(dsc, rs, 1, defer=True)
+        assert ticket3 >= 0 and flags3 == flags1
+        cabi.check(L.b200gs_context_backward(ctx.h, C.byref(prm3), C.c_int32(flags3), p(rs.bg), p(rs.viewmatrix), p(rs.projmatrix),
+                                             p(rs.campos), p(dsc["means3D"]), p(dsc["shs"]), None, p(dsc["opacities"]),
+                                             p(dsc["scales"]), p(dsc["rotations"]), None, p(radii3), None, None, None,
+                                             C.c_int32(1), p(dL), p(g_def["means3D"]), p(g2d_def), p(g_def["shs"]), None,
+                                             p(g_def["opacities"]), p(g_def["scales"]), p(g_def["rotations"]), None,
+                                             C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        D3, ok3 = ctx.wait(ticket3)
+        assert ok3 and D3 == D1
+        torch.cuda.synchronize()
+        assert torch.equal(color3, color1)
+        for k in ("means3D", "shs", "opacities", "scales", "rotations"):
+            r = getattr(ref, k)
+            assert max_rel_err(g_def[k].cpu().numpy().reshape(r.shape), r) < 1e-3, k
         # B200GS_FORWARD_ONLY travels through the context: same frame, same radii, and the adjoint refuses to run on it
         color2, radii2, D2, _, flags2, prm2 = ctx.forward(dsc, rs, 1, flags=cabi.FORWARD_ONLY)
         torch.cuda.synchronize()
