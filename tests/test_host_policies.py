@@ -82,3 +82,53 @@ def test_frames_in_flight_follow_the_ranks_on_the_box():
     # device->host path of the box is the bound and more frames in flight only add concurrent copies
     from robosimgs_b200.sweep import host_frames_in_flight
     assert [host_frames_in_flight(n) for n in (1, 2, 4, 8)] == [6, 6, 4, 4]
+
+
+def test_backward_or_retry_repeats_an_overflowed_step_and_gives_up_after_the_retries():
+    """train.backward_or_retry: a step whose backward reports PairCapacityExceeded (the deferred training mode of the
+    rasterizer) is rendered again; other errors and a persistent overflow propagate."""
+    import pytest
+    from robosimgs_b200 import PairCapacityExceeded
+    from robosimgs_b200.train import backward_or_retry
+
+    class Overflowing(torch.autograd.Function):
+        fails_left = 0
+
+        @staticmethod
+        def forward(ctx, x):
+            return x * 2.0
+
+        @staticmethod
+        def backward(ctx, g):
+            if Overflowing.fails_left > 0:
+                Overflowing.fails_left -= 1
+                raise PairCapacityExceeded("9 pairs, capacity 4: run the step again")
+            return g * 2.0
+
+    x = torch.ones(3, requires_grad=True)
+    calls = []
+
+    def loss_fn(scale):
+        calls.append(scale)
+        return (Overflowing.apply(x) * scale).sum()
+
+    Overflowing.fails_left = 2
+    loss = backward_or_retry(loss_fn, 0.5, retries=2)
+    assert len(calls) == 3 and float(loss) == 3.0
+    assert torch.equal(x.grad, torch.ones(3))            # only the step that completed reached the leaf
+    x.grad = None
+    Overflowing.fails_left = 3
+    with pytest.raises(PairCapacityExceeded):
+        backward_or_retry(loss_fn, 0.5, retries=2)
+    assert x.grad is None
+    assert issubclass(PairCapacityExceeded, rz._cabi.B200GSError)
+
+
+def test_defer_options_carry_the_training_and_rgb8_switches():
+    o = rz.DeferOptions()
+    assert o.train is False and o.rgb8 is None and o.capacity == 0 and o.record_event
+    buf = torch.empty((4, 6, 3), dtype=torch.uint8)
+    o = rz.DeferOptions(train=True, rgb8=buf)
+    assert o.train and o.rgb8 is buf and len(o) == 0
+    r = rz.GaussianRasterizer(None)
+    assert r.defer_pair_check is False and r.last_ticket is None       # the operator's default contract: blocking
