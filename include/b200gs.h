@@ -290,7 +290,9 @@ int b200gs_context_query(B200GSContext* ctx, int32_t P, int32_t image_height, in
  * highest priority, compositing and the 8-bit export the lowest, and the graph is instantiated with
  * cudaGraphInstantiateFlagUseNodePriority: with several frames in flight on different streams one frame's short,
  * latency-bound binning chain runs underneath another frame's compositing instead of queueing behind its CTAs.
- * mode 2: as 1 with a middle priority for the chain.  Results are identical.  *exec_out is a cudaGraphExec_t;
+ * mode 2: as 1 with a middle priority for the chain.  Results are identical.  Modes 1 and 2 set the priority attribute
+ * on the kernel nodes of `graph` itself (the caller's graph is modified, not copied); the graph stays the caller's and
+ * must outlive nothing -- the executable graph is self-contained.  *exec_out is a cudaGraphExec_t;
  * n_low / n_high (optional) receive the number of kernel nodes marked low / high.
  */
 int b200gs_graph_instantiate(void* graph, int32_t mode, void** exec_out, int32_t* n_low, int32_t* n_high);
