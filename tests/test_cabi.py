@@ -75,3 +75,51 @@ def test_product_never_imports_oracle():
                 if f.endswith((".py", ".cu", ".cuh", ".h", ".sh")):
                     txt = open(os.path.join(dirpath, f)).read()
                     assert "import oracle" not in txt and "from oracle" not in txt and "gs_oracle.h" not in txt, (top, f)
+
+
+def test_header_is_plain_c_and_a_c_host_links_and_runs(built, tmp_path):
+    """The drop-in boundary is a C ABI: include/b200gs.h must compile as strict C99 (no C++-isms), a C host must link
+    against libb200gs.so taking the address of every declared entry point, and the host-only calls must work from C
+    (version, policy rules, buffer sizes, error string) -- no device needed."""
+    import shutil
+    import subprocess
+    from robosimgs_b200 import _cabi
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    syms = _declared_symbols()
+    table = ",\n    ".join(f'{{"{s}", (void (*)(void))&{s}}}' for s in syms)
+    src = tmp_path / "c_host.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "b200gs.h"
+struct entry { const char* name; void (*fn)(void); };
+static const struct entry table[] = {
+    %s
+};
+int main(void) {
+  size_t n = sizeof(table) / sizeof(table[0]), i, g = 0, b = 0, im = 0;
+  B200GSParams prm;
+  B200GSAlloc a;
+  memset(&prm, 0, sizeof prm);
+  memset(&a, 0, sizeof a);
+  for (i = 0; i < n; i++) if (!table[i].fn) return 2;
+  if (b200gs_version() != B200GS_VERSION) return 3;
+  if (b200gs_policy_pair_capacity(0) != 0 || b200gs_policy_pair_capacity(160000) != 160000 + 10000 + 32768) return 4;
+  if (b200gs_buffer_sizes(1000, 1080, 1920, 50000, &g, &b, &im) != 0 || g == 0 || b == 0 || im == 0) return 5;
+  if (b200gs_buffer_sizes(-1, 10, 10, 0, NULL, NULL, NULL) == 0 || !strstr(b200gs_last_error(), "invalid")) return 6;
+  if ((B200GS_DEFER_PAIR_CHECK | B200GS_FORWARD_ONLY | B200GS_OUT_RGB8) != 7 || B200GS_BIN_SHIFT_HINT(3) != 0x400) return 7;
+  printf("%%u entry points, params %%u bytes\n", (unsigned)n, (unsigned)sizeof prm);
+  return 0;
+}
+''' % table)
+    exe = tmp_path / "c_host"
+    libdir = os.path.dirname(_cabi.LIB_PATH)
+    cmd = [cc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src),
+           "-o", str(exe), "-L", libdir, "-l:libb200gs.so", f"-Wl,-rpath,{libdir}", "-Wl,-rpath,/usr/local/cuda/lib64"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert r.stdout.startswith(f"{len(syms)} entry points") and f"{ctypes.sizeof(_cabi.B200GSParams)} bytes" in r.stdout
