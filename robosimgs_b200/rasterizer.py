@@ -302,8 +302,15 @@ class _RasterizeGaussians(torch.autograd.Function):
         pol, shift_used, bin_flags = _bin_flags(hint_key, H, W)
         # a deferred frame is forward-only by construction: the per-pixel state of the adjoint (20 B per pixel) is not
         # written unless the caller wants the alpha channel, which is read from it
-        keep_state = want_alpha or (ticket_box is not None and opts.train)
-        fwd_flags = ((_cabi.DEFER_PAIR_CHECK | (0 if keep_state else _cabi.FORWARD_ONLY)) if defer else 0)
+        # -- and so is a blocking frame nobody can differentiate (no_grad, or no input requires a gradient), unless
+        # the bin-size policy is about to read the frame's coverage from that state (first and every 256th call)
+        needs_grad = bool(grad_mode) and any(ctx.needs_input_grad)
+        policy_looks = ADAPT_BIN_SIZE and not rs.debug and ((pol["calls"] + 1) == 1 or (pol["calls"] + 1) % 256 == 0)
+        if defer:
+            keep_state = want_alpha or opts.train
+        else:
+            keep_state = want_alpha or needs_grad or policy_looks
+        fwd_flags = (_cabi.DEFER_PAIR_CHECK if defer else 0) | (0 if keep_state else _cabi.FORWARD_ONLY)
         rgb8 = opts.rgb8 if ticket_box is not None else None
         if rgb8 is not None:
             if rgb8.dtype != torch.uint8 or tuple(rgb8.shape) != (H, W, 3) or rgb8.device != dev or not rgb8.is_contiguous():
