@@ -182,6 +182,14 @@ def test_context_backward_matches_oracle_and_bin_policy_never_changes_results():
         torch.cuda.synchronize()
         assert flags2 == (flags1 | cabi.FORWARD_ONLY) and D2 == D1
         assert torch.equal(color2, color1) and torch.equal(radii2, radii)
+        # ... and so does B200GS_OUT_RGB8: the first H*W*3 bytes of the output buffer are the 8-bit frame
+        from robosimgs_b200 import export_rgb8
+        color4, _, _, _, flags4, _ = ctx.forward(dsc, rs, 1, flags=cabi.FORWARD_ONLY | cabi.OUT_RGB8)
+        torch.cuda.synchronize()
+        assert flags4 == (flags1 | cabi.FORWARD_ONLY | cabi.OUT_RGB8)
+        H_, W_ = rs.image_height, rs.image_width
+        frame8 = color4.view(torch.uint8).reshape(-1)[: H_ * W_ * 3].view(H_, W_, 3)
+        assert torch.equal(frame8, export_rgb8(color1))
         with pytest.raises(cabi.B200GSError, match="FORWARD_ONLY"):
             cabi.check(L.b200gs_context_backward(ctx.h, C.byref(prm2), C.c_int32(flags2), p(rs.bg), p(rs.viewmatrix),
                                                  p(rs.projmatrix), p(rs.campos), p(dsc["means3D"]), p(dsc["shs"]), None,
