@@ -504,6 +504,11 @@ class GaussianRasterizer(nn.Module):
         out = rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
                                   cov3D_precomp, rs, self.scratch_tag, box)
         if box is not None:
+            # a frame whose backward never ran (evaluation with grad enabled) still gives its pinned word back and
+            # feeds the capacity hint, as soon as its stream has passed it
+            old = self.last_ticket
+            if old is not None and old._ok is None and (old.event is None or old.event.query()):
+                old.ok()
             self.last_ticket = box[-1]
         return out
 
